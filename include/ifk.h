@@ -1,0 +1,119 @@
+/*
+ * ifk.h -- C ABI of the B200 inverse-convolution kernels ("ifk" = inverse-flow kernels).
+ *
+ * This is the drop-in boundary for the ONE hot path this repository replaces: the
+ * `inv_conv_with_bp` CUDA extension of girish-lab/Inverse-Flow, i.e. the four entry points
+ * exported at inf/utils/inv_conv_cuda/inv_conv_with_bp_general.cpp:115-120
+ * (`inverse`, `forward`, `dy`, `dw`) and called from inf/layers/inv_conv.py:52,74,79,266,459.
+ *
+ * Conventions (all functions):
+ *   - plain C, no torch / ATen types; every pointer is a DEVICE pointer to float32 data
+ *     owned by the caller; nothing is allocated, freed or retained by the library;
+ *   - tensors are NCHW-contiguous (the layout the reference passes, inv_conv.py:45-60);
+ *     the weight is (C, Cw, KH, KW) contiguous with Cw >= C/groups -- the reference layers
+ *     pass Cw == C and the kernels read the first C/groups input columns of each row
+ *     (inv_conv_with_bp_kernel_general.cu:62);
+ *   - work is enqueued on the caller's stream and the call returns immediately: no device
+ *     synchronisation (the reference calls cudaDeviceSynchronize() per diagonal, .cu:124),
+ *     graph-capturable, re-entrant, no global state;
+ *   - return value: 0 = ok, negative = IFK_ERR_* argument error (nothing was launched),
+ *     positive = a cudaError_t raised by a launch.
+ *
+ * Math contract.  With Cg = C/groups, `base` the first channel of
+ * c's group and w[c][kc][q] := W[c][kc][KH-1-qh][KW-1-qw] for a shift q = (qh, qw):
+ *
+ *   (L y)[b,c,p] = y[b,c,p] + sum_{(q,kc) != (0,c-base), kc < c-base when q == 0}
+ *                                 w[c][kc][q] * y[b, base+kc, p-q]        (zero outside)
+ *
+ * i.e. a causal (top-left zero padded) masked convolution with an implicit unit diagonal
+ * and a strictly-lower-triangular centre tap.  `groups == 1` is the semantics of the
+ * reference's CPU solvers (inf/utils/solve_mc.py:88-114, fastflow_inverse/
+ * solve_parallel_mc.pyx:100-124, cinc_kernel_level1.cu:57-69); `groups == 4` that of
+ * cinc_kernel_level2.cu:59-72 and, for C == 4, of the shipped inv_conv_with_bp kernels.
+ */
+#ifndef IFK_H
+#define IFK_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFK_VERSION 100 /* major*10000 + minor*100 + patch */
+
+/* cudaStream_t without the CUDA headers (a driver-level CUstream handle). */
+typedef struct CUstream_st *ifk_stream_t;
+
+enum ifk_status {
+    IFK_OK = 0,
+    IFK_ERR_NULL_POINTER = -1,  /* a required pointer is NULL                            */
+    IFK_ERR_BAD_SHAPE = -2,     /* a dimension is negative, or C/H/W/KH/KW is zero        */
+    IFK_ERR_BAD_GROUPS = -3,    /* groups < 1, C % groups != 0 or Cw < C/groups          */
+    IFK_ERR_UNSUPPORTED = -4,   /* shape exceeds what the kernels address */
+    IFK_ERR_NO_DEVICE = -5      /* no CUDA device / driver                               */
+};
+
+/* Geometry of one call.  B may be 0 (the call is a no-op that still validates). */
+typedef struct ifk_problem {
+    int B, C, H, W; /* activations: (B, C, H, W)                                */
+    int KH, KW;     /* kernel taps                                              */
+    int Cw;         /* second dimension of the weight tensor, >= C / groups     */
+    int groups;     /* channel groups; the reference kernels hard-code 4        */
+} ifk_problem;
+
+int ifk_version(void);
+const char *ifk_status_string(int status);
+
+/* ---- prepared weights ---------------------------------------------------------------
+ * The solve kernels consume a "prepared" copy of the weight: per group, the non-centre
+ * taps pre-multiplied by T = (I + A0)^-1 (A0 = the strictly-lower centre tap) and negated,
+ * for the forward solve (L^-1) and, transposed, for the adjoint solve (L^-T).  Folding T
+ * removes the per-pixel Cg-step channel substitution from the wavefront's critical path.
+ * One ifk_prepare_f32 call serves one ifk_inverse_f32 and the matching ifk_backward_f32.
+ * `prepared` must hold ifk_prepared_floats(p) floats. */
+size_t ifk_prepared_floats(const ifk_problem *p);
+int ifk_prepare_f32(const ifk_problem *p, const float *weight, float *prepared,
+                    ifk_stream_t stream);
+
+/* y = L^-1 x : the layer's training direction x -> z.
+ * Replaces inv_conv_with_bp.inverse (inv_conv_with_bp_general.cpp:19-28 ->
+ * inv_conv_cuda_inverse, inv_conv_with_bp_kernel_general.cu:72-129).  x and y may alias. */
+int ifk_inverse_f32(const ifk_problem *p, const float *x, const float *prepared, float *y,
+                    ifk_stream_t stream);
+
+/* x = L y : the masked convolution, sampling direction z -> x.
+ * Replaces inv_conv_with_bp.forward (inv_conv_with_bp_general.cpp:44-53 ->
+ * inv_conv_fwd_cuda_inverse, .cu:203-264).  Takes the RAW weight.  x and y must not alias. */
+int ifk_conv_f32(const ifk_problem *p, const float *y, const float *weight, float *x,
+                 ifk_stream_t stream);
+
+/* dX = L^-T g : gradient w.r.t. the layer input.
+ * Replaces inv_conv_with_bp.dy (inv_conv_with_bp_general.cpp:70-81 -> inv_conv_dy,
+ * .cu:388-483), computing the true adjoint.  g and dx may alias. */
+int ifk_bwd_input_f32(const ifk_problem *p, const float *g, const float *prepared, float *dx,
+                      ifk_stream_t stream);
+
+/* dW[c][kc][KH-1-qh][KW-1-qw] = - sum_{b,p} dX[b,c,p] * y[b,base+kc,p-q]; masked taps and
+ * columns kc >= C/groups are written as 0.  `y` is the saved OUTPUT of ifk_inverse_f32.
+ * Replaces inv_conv_with_bp.dw (inv_conv_with_bp_general.cpp:99-112 -> inv_conv_dw,
+ * .cu:634-735).  Deterministic: per-CTA partial sums in `workspace`, reduced in a fixed
+ * order.  `workspace` must hold ifk_bwd_weight_workspace_bytes(p) bytes (16-byte aligned). */
+size_t ifk_bwd_weight_workspace_bytes(const ifk_problem *p);
+int ifk_bwd_weight_f32(const ifk_problem *p, const float *dx, const float *y, float *dw,
+                       void *workspace, ifk_stream_t stream);
+
+/* dX and dW in one call (what inv_conv_.backward needs, inv_conv.py:62-81). */
+int ifk_backward_f32(const ifk_problem *p, const float *g, const float *y,
+                     const float *prepared, float *dx, float *dw, void *workspace,
+                     ifk_stream_t stream);
+
+/* ---- introspection (used by bench.py / tests; not needed by a binding) -----------------
+ * Which kernel variant a solve of this geometry dispatches to, as a short static string,
+ * e.g. "smem<cc=3,chunk=27> ns=4 slots=16 threads=256 smem=24KB" or "global". */
+int ifk_describe_solve(const ifk_problem *p, char *buf, size_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFK_H */

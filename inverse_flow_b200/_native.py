@@ -1,0 +1,85 @@
+"""ctypes binding of the C ABI (include/ifk.h) -> inverse_flow_b200/lib/libifk_b200.so.
+
+torch is used here only for device memory and the current stream; every compute call goes
+through the C ABI with raw device pointers.  ctypes releases the GIL for the duration of
+each foreign call (the reference's pybind module holds it).
+
+There is NO fallback: if the library is missing or fails to load this raises, and so does
+every op on a machine without a CUDA device.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libifk_b200.so")
+
+EXPORTS = (
+    "ifk_version", "ifk_status_string", "ifk_prepared_floats", "ifk_prepare_f32",
+    "ifk_inverse_f32", "ifk_conv_f32", "ifk_bwd_input_f32", "ifk_bwd_weight_workspace_bytes",
+    "ifk_bwd_weight_f32", "ifk_backward_f32", "ifk_describe_solve",
+)
+
+
+class Problem(ctypes.Structure):
+    """struct ifk_problem"""
+    _fields_ = [(n, ctypes.c_int) for n in ("B", "C", "H", "W", "KH", "KW", "Cw", "groups")]
+
+
+class IfkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises IfkError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IfkError(
+            "native library %s not found: run `python -m inverse_flow_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    P, vp, sz, ci = ctypes.POINTER(Problem), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.ifk_version.restype = ci
+    lib.ifk_status_string.restype = ctypes.c_char_p
+    lib.ifk_status_string.argtypes = [ci]
+    lib.ifk_prepared_floats.restype = sz
+    lib.ifk_prepared_floats.argtypes = [P]
+    lib.ifk_bwd_weight_workspace_bytes.restype = sz
+    lib.ifk_bwd_weight_workspace_bytes.argtypes = [P]
+    for name, nptr in (("ifk_prepare_f32", 2), ("ifk_inverse_f32", 3), ("ifk_conv_f32", 3),
+                       ("ifk_bwd_input_f32", 3), ("ifk_bwd_weight_f32", 4), ("ifk_backward_f32", 6)):
+        fn = getattr(lib, name)
+        fn.restype = ci
+        fn.argtypes = [P] + [vp] * nptr + [vp]          # ..., stream
+    lib.ifk_describe_solve.restype = ci
+    lib.ifk_describe_solve.argtypes = [P, ctypes.c_char_p, sz]
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().ifk_status_string(status).decode()
+        if status < 0:
+            raise ValueError("ifk: %s (status %d)" % (msg, status))
+        raise IfkError("ifk: CUDA error %d: %s" % (status, msg))
+
+
+def problem(B, C, H, W, KH, KW, Cw, groups):
+    return Problem(int(B), int(C), int(H), int(W), int(KH), int(KW), int(Cw), int(groups))
+
+
+def current_stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def describe_solve(p):
+    buf = ctypes.create_string_buffer(256)
+    check(load().ifk_describe_solve(ctypes.byref(p), buf, 256))
+    return buf.value.decode()

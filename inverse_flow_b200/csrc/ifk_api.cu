@@ -1,0 +1,131 @@
+// extern "C" boundary (include/ifk.h): argument validation and dispatch only.
+#include <stdio.h>
+#include "ifk_internal.cuh"
+
+namespace ifk {
+
+int make_geometry(const ifk_problem *p, Geometry *g)
+{
+    if (!p) return IFK_ERR_NULL_POINTER;
+    if (p->B < 0 || p->C <= 0 || p->H <= 0 || p->W <= 0 || p->KH <= 0 || p->KW <= 0 || p->Cw <= 0)
+        return IFK_ERR_BAD_SHAPE;
+    if (p->groups < 1 || p->C % p->groups != 0 || p->Cw < p->C / p->groups) return IFK_ERR_BAD_GROUPS;
+    g->B = p->B; g->C = p->C; g->H = p->H; g->W = p->W; g->KH = p->KH; g->KW = p->KW;
+    g->Cw = p->Cw; g->groups = p->groups;
+    g->Cg = p->C / p->groups;
+    g->K = p->KH * p->KW;
+    // 32-bit index arithmetic inside one image / one weight tensor
+    const long long per_image = (long long)p->C * p->H * p->W;
+    const long long wsize = (long long)p->C * p->Cw * g->K;
+    const long long kd = (long long)g->K * g->Cg;
+    if (per_image >= (1LL << 30) || wsize >= (1LL << 30) || kd >= (1LL << 24) || p->groups > 65535)
+        return IFK_ERR_UNSUPPORTED;
+    g->KD = (int)kd;
+    g->KDP = round_up(g->KD, 4);
+    if ((size_t)g->Cg * g->Cg * sizeof(float) > (size_t)kMaxSmemBytes) return IFK_ERR_UNSUPPORTED;
+    return IFK_OK;
+}
+
+}  // namespace ifk
+
+using namespace ifk;
+
+extern "C" {
+
+int ifk_version(void) { return IFK_VERSION; }
+
+const char *ifk_status_string(int status)
+{
+    switch (status) {
+        case IFK_OK: return "ok";
+        case IFK_ERR_NULL_POINTER: return "a required pointer is NULL";
+        case IFK_ERR_BAD_SHAPE: return "bad shape: negative dimension or zero C/H/W/KH/KW/Cw";
+        case IFK_ERR_BAD_GROUPS: return "bad groups: need groups >= 1, C % groups == 0, Cw >= C/groups";
+        case IFK_ERR_UNSUPPORTED: return "shape not supported by the kernels";
+        case IFK_ERR_NO_DEVICE: return "no CUDA device";
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "unknown ifk status";
+}
+
+size_t ifk_prepared_floats(const ifk_problem *p)
+{
+    Geometry g;
+    if (make_geometry(p, &g) != IFK_OK) return 0;
+    return prepared_floats(g);
+}
+
+int ifk_prepare_f32(const ifk_problem *p, const float *weight, float *prepared, ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!weight || !prepared) return IFK_ERR_NULL_POINTER;
+    return launch_prepare(g, weight, prepared, (cudaStream_t)stream);
+}
+
+int ifk_inverse_f32(const ifk_problem *p, const float *x, const float *prepared, float *y,
+                    ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!prepared || (g.B > 0 && (!x || !y))) return IFK_ERR_NULL_POINTER;
+    return launch_solve(g, x, prepared_dir(g, prepared, 0), y, false, (cudaStream_t)stream);
+}
+
+int ifk_conv_f32(const ifk_problem *p, const float *y, const float *weight, float *x,
+                 ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!weight || (g.B > 0 && (!x || !y))) return IFK_ERR_NULL_POINTER;
+    return launch_conv(g, y, weight, x, (cudaStream_t)stream);
+}
+
+int ifk_bwd_input_f32(const ifk_problem *p, const float *grad, const float *prepared, float *dx,
+                      ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!prepared || (g.B > 0 && (!grad || !dx))) return IFK_ERR_NULL_POINTER;
+    return launch_solve(g, grad, prepared_dir(g, prepared, 1), dx, true, (cudaStream_t)stream);
+}
+
+size_t ifk_bwd_weight_workspace_bytes(const ifk_problem *p)
+{
+    Geometry g;
+    if (make_geometry(p, &g) != IFK_OK) return 0;
+    return bwd_weight_workspace_bytes(g);
+}
+
+int ifk_bwd_weight_f32(const ifk_problem *p, const float *dx, const float *y, float *dw,
+                       void *workspace, ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!dw || !workspace || (g.B > 0 && (!dx || !y))) return IFK_ERR_NULL_POINTER;
+    return launch_bwd_weight(g, dx, y, dw, workspace, (cudaStream_t)stream);
+}
+
+int ifk_backward_f32(const ifk_problem *p, const float *grad, const float *y, const float *prepared,
+                     float *dx, float *dw, void *workspace, ifk_stream_t stream)
+{
+    int st = ifk_bwd_input_f32(p, grad, prepared, dx, stream);
+    if (st != IFK_OK) return st;
+    return ifk_bwd_weight_f32(p, dx, y, dw, workspace, stream);
+}
+
+int ifk_describe_solve(const ifk_problem *p, char *buf, size_t buflen)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!buf || buflen == 0) return IFK_ERR_NULL_POINTER;
+    return describe_solve(g, buf, buflen);
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+// Internal declarations shared by the kernel translation units.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ifk.h"
+
+namespace ifk {
+
+constexpr int kNumSM = 148;               // B200: 2 dies x 74 SMs
+constexpr int kMaxSmemBytes = 227 * 1024; // opt-in dynamic shared memory per CTA
+
+struct Geometry {
+    int B, C, H, W, KH, KW, Cw, groups;
+    int Cg;   // channels per group
+    int K;    // KH * KW taps (tap 0 = the centre / "x" tap)
+    int KD;   // K * Cg : length of one prepared weight row
+    int KDP;  // KD rounded up to a multiple of 4 (row stride of the prepared weight)
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int make_geometry(const ifk_problem *p, Geometry *g);          // validates; IFK_ERR_* or 0
+inline size_t prepared_floats(const Geometry &g) { return (size_t)2 * g.C * g.KDP; }
+inline const float *prepared_dir(const Geometry &g, const float *prepared, int dir) {
+    return prepared + (size_t)dir * g.C * g.KDP;
+}
+
+// launchers (each returns 0 or a cudaError_t)
+int launch_prepare(const Geometry &g, const float *weight, float *prepared, cudaStream_t s);
+int launch_solve(const Geometry &g, const float *in, const float *prep_dir, float *out,
+                 bool reverse, cudaStream_t s);
+int launch_conv(const Geometry &g, const float *y, const float *weight, float *x, cudaStream_t s);
+size_t bwd_weight_workspace_bytes(const Geometry &g);
+int launch_bwd_weight(const Geometry &g, const float *dx, const float *y, float *dw,
+                      void *workspace, cudaStream_t s);
+int describe_solve(const Geometry &g, char *buf, size_t buflen);
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
+
+}  // namespace ifk

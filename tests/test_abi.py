@@ -1,0 +1,90 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/ifk.h
+declares, and validates arguments before touching the device (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from inverse_flow_b200 import _native
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from inverse_flow_b200.build import build_native
+    build_native()
+    return _native.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ifk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ifk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = declared_symbols()
+    assert set(names) == set(_native.EXPORTS), "keep _native.EXPORTS in sync with include/ifk.h"
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+
+
+def test_version_and_status_strings(lib):
+    assert lib.ifk_version() == 100
+    assert lib.ifk_status_string(0) == b"ok"
+    for code in (-1, -2, -3, -4, -5):
+        assert lib.ifk_status_string(code) not in (b"ok", b"unknown ifk status")
+
+
+def test_sizes(lib):
+    p = _native.problem(100, 12, 16, 16, 3, 3, 12, 1)
+    # 2 directions x C rows x round_up(K*Cg, 4)
+    assert lib.ifk_prepared_floats(ctypes.byref(p)) == 2 * 12 * 108
+    p4 = _native.problem(100, 12, 16, 16, 3, 3, 12, 4)
+    assert lib.ifk_prepared_floats(ctypes.byref(p4)) == 2 * 12 * 28
+    ws = lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(p))
+    assert ws > 0 and ws % (12 * 12 * 9 * 4) == 0
+
+
+@pytest.mark.parametrize("kwargs,code", [
+    (dict(C=0), -2), (dict(H=0), -2), (dict(KH=0), -2), (dict(B=-1), -2),
+    (dict(groups=0), -3), (dict(groups=5), -3), (dict(groups=4, Cw=2), -3),
+])
+def test_bad_geometry_is_rejected_before_any_launch(lib, kwargs, code):
+    base = dict(B=2, C=12, H=8, W=8, KH=3, KW=3, Cw=12, groups=1)
+    base.update(kwargs)
+    p = _native.problem(**base)
+    dummy = ctypes.c_void_p(16)
+    assert lib.ifk_inverse_f32(ctypes.byref(p), dummy, dummy, dummy, None) == code
+    assert lib.ifk_conv_f32(ctypes.byref(p), dummy, dummy, dummy, None) == code
+    assert lib.ifk_prepared_floats(ctypes.byref(p)) == 0
+    with pytest.raises(ValueError):
+        _native.check(code)
+
+
+def test_null_pointers_are_rejected(lib):
+    p = _native.problem(2, 4, 5, 5, 3, 3, 4, 1)
+    dummy = ctypes.c_void_p(16)
+    assert lib.ifk_inverse_f32(ctypes.byref(p), None, dummy, dummy, None) == -1
+    assert lib.ifk_inverse_f32(None, dummy, dummy, dummy, None) == -1
+    assert lib.ifk_bwd_weight_f32(ctypes.byref(p), dummy, dummy, dummy, None, None) == -1
+    assert lib.ifk_prepare_f32(ctypes.byref(p), None, dummy, None) == -1
+
+
+def test_empty_batch_is_a_noop_on_the_solve(lib):
+    p = _native.problem(0, 4, 5, 5, 3, 3, 4, 1)
+    dummy = ctypes.c_void_p(16)
+    assert lib.ifk_inverse_f32(ctypes.byref(p), None, dummy, None, None) == 0
+    assert lib.ifk_bwd_input_f32(ctypes.byref(p), None, dummy, None, None) == 0
+    assert lib.ifk_conv_f32(ctypes.byref(p), None, dummy, None, None) == 0
+
+
+def test_describe_solve_picks_the_resident_kernel_for_model_shapes(lib):
+    for shape in [(100, 4, 14, 14, 2), (100, 8, 7, 7, 2), (64, 1, 28, 28, 3), (100, 12, 16, 16, 3),
+                  (100, 24, 8, 8, 3), (100, 48, 4, 4, 3)]:
+        B, C, H, W, k = shape
+        d = _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1))
+        assert d.startswith("smem<"), (shape, d)
+    big = _native.describe_solve(_native.problem(8, 96, 64, 64, 7, 7, 96, 1))
+    assert big.startswith("global")

@@ -1,0 +1,298 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): float32 results within max relative error 1e-5 of the
+reference semantics, where max relative error := max|a - ref| / max|ref| with ref the
+float64 oracle (oracle.max_rel_err); conv(inverse(x)) reconstruction error reported too.
+Weights follow the reference initialisation (small taps); a few cases use larger taps.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_weight
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def IF():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from inverse_flow_b200 import functional
+    return functional
+
+
+def dev(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
+
+
+def run_all(IF, x, w, g, groups):
+    """inverse, conv, dX, dW on the GPU; float64 oracle beside it.  Returns error dict."""
+    xd, wd, gd = dev(x), dev(w), dev(g)
+    y = IF.inverse(xd, wd, groups=groups)
+    rec = IF.conv(y, wd, groups=groups)
+    dx, dw = IF.backward(gd, y, wd, groups=groups)
+    torch.cuda.synchronize()
+    x64, w64, g64 = (np.asarray(a, dtype=np.float64) for a in (x.astype(np.float32), w.astype(np.float32),
+                                                                g.astype(np.float32)))
+    y_ref = oracle.inverse(x64, w64, groups, threads=4)
+    dx_ref, dw_ref = oracle.backward(g64, y_ref, w64, groups, threads=4)
+    return {
+        "y": oracle.max_rel_err(y.cpu().numpy(), y_ref),
+        "rec": oracle.max_rel_err(rec.cpu().numpy(), x64),
+        "conv": oracle.max_rel_err(rec.cpu().numpy(), oracle.conv(y.cpu().numpy().astype(np.float64), w64, groups)),
+        "dx": oracle.max_rel_err(dx.cpu().numpy(), dx_ref),
+        "dw": oracle.max_rel_err(dw.cpu().numpy(), dw_ref),
+        "dw_masked_zero": bool(np.all(dw.cpu().numpy()[dw_ref == 0.0] == 0.0)),
+    }
+
+
+def assert_parity(err, tol=TOL):
+    for k in ("y", "rec", "conv", "dx", "dw"):
+        assert err[k] < tol, (k, err)
+    assert err["dw_masked_zero"], err
+
+
+def test_golden_vectors(IF, golden):
+    """outputs of the reference itself (tests/golden/make_golden.py)."""
+    x, w, g, groups = golden["x"], golden["w"], golden["g"], golden["groups"]
+    xd, wd, gd = dev(x), dev(w), dev(g)
+    y = IF.inverse(xd, wd, groups=groups)
+    assert oracle.max_rel_err(y.cpu().numpy(), golden["y_solve"]) < TOL
+    assert oracle.max_rel_err(IF.conv(dev(golden["y_solve"]), wd, groups=groups).cpu().numpy(),
+                              golden["conv_of_y"]) < TOL
+    dx, dw = IF.backward(gd, dev(golden["y_solve"]), wd, groups=groups)
+    assert oracle.max_rel_err(dx.cpu().numpy(), golden["dx_ref"]) < TOL
+    assert oracle.max_rel_err(dw.cpu().numpy(), golden["dw_ref_fd"]) < TOL
+    # separate entry points agree with the fused one bit for bit
+    dx2 = IF.bwd_input(gd, wd, groups=groups)
+    dw2 = IF.bwd_weight(dx2, dev(golden["y_solve"]), wd, groups=groups)
+    assert torch.equal(dx, dx2) and torch.equal(dw, dw2)
+
+
+# (B, C, H, W, KH, KW, groups, tap scale): BASELINE model shapes, the reference test shape,
+# ragged / degenerate cases
+SHAPES = [
+    (64, 1, 28, 28, 3, 3, 1, 0.05),       # configs[0]: if_cnn_mnist
+    (100, 4, 14, 14, 2, 2, 1, 0.05),      # if_glow_mnist stage 1
+    (100, 4, 14, 14, 2, 2, 4, 0.05),
+    (100, 8, 7, 7, 2, 2, 1, 0.05),        # if_glow_mnist stage 2
+    (100, 8, 7, 7, 2, 2, 4, 0.05),
+    (32, 12, 16, 16, 3, 3, 1, 0.02),      # cifar / imagenet32 level 1
+    (32, 12, 16, 16, 3, 3, 4, 0.02),
+    (32, 24, 8, 8, 3, 3, 1, 0.02),
+    (32, 24, 8, 8, 3, 3, 4, 0.02),
+    (32, 48, 4, 4, 3, 3, 1, 0.02),
+    (32, 48, 4, 4, 3, 3, 4, 0.02),
+    (1, 4, 5, 5, 3, 3, 4, 0.01),          # tests/inf/test_layers.py:182-190
+    (3, 3, 16, 16, 5, 5, 1, 0.02),
+    (2, 3, 9, 13, 3, 3, 1, 0.1),          # H != W
+    (2, 5, 13, 9, 2, 3, 1, 0.1),          # KH != KW, odd channel count
+    (2, 6, 10, 10, 3, 3, 2, 0.05),
+    (2, 6, 10, 10, 3, 3, 3, 0.05),
+    (4, 7, 1, 1, 3, 3, 1, 0.2),           # single pixel: only the centre tap acts
+    (2, 4, 1, 17, 3, 3, 1, 0.1),          # single row
+    (2, 4, 17, 1, 3, 3, 1, 0.1),          # single column
+    (2, 4, 6, 6, 1, 1, 1, 0.2),           # 1x1 kernel: pure channel triangular solve
+    (2, 2, 12, 12, 7, 7, 1, 0.01),        # kernel larger than half the image
+    (1, 1, 3, 3, 5, 5, 1, 0.05),          # kernel larger than the image
+    (5, 16, 32, 32, 3, 3, 1, 0.01),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s[:7])))
+def test_parity_against_oracle(IF, shape):
+    B, C, H, W, KH, KW, groups, scale = shape
+    rng = np.random.default_rng(hash(shape[:7]) % (2 ** 31))
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, KH, KW, scale)
+    assert_parity(run_all(IF, x, w, g, groups))
+
+
+@pytest.mark.parametrize("shape", [(3, 12, 16, 16, 3, 3, 1, 0.02), (2, 8, 7, 7, 2, 2, 4, 0.05),
+                                   (2, 3, 9, 13, 3, 3, 1, 0.1), (2, 5, 13, 9, 2, 3, 1, 0.1)],
+                         ids=lambda s: "x".join(map(str, s[:7])))
+def test_global_fallback_kernel(IF, shape, monkeypatch):
+    """Force the kernel used for images that do not fit in shared memory."""
+    monkeypatch.setenv("IFK_SOLVE_GLOBAL", "1")
+    B, C, H, W, KH, KW, groups, scale = shape
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, KH, KW, scale)
+    assert_parity(run_all(IF, x, w, g, groups))
+
+
+def test_large_image_takes_the_global_path(IF):
+    """(2, 48, 32, 32) k=5 does not fit in shared memory (and dW runs unstaged)."""
+    rng = np.random.default_rng(5)
+    B, C, H, W, k = 2, 48, 32, 32, 5
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, k, k, 0.005)
+    assert_parity(run_all(IF, x, w, g, 1))
+
+
+def test_weight_with_fewer_input_columns(IF):
+    """groups=4 only reads W[:, :C/4]; a (C, C/4, k, k) weight must give the same result."""
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((4, 8, 6, 6)).astype(np.float32)
+    w = make_weight(rng, 8, 8, 3, 3, 0.05)
+    a = IF.inverse(dev(x), dev(w), groups=4)
+    b = IF.inverse(dev(x), dev(w[:, :2]), groups=4)
+    assert torch.equal(a, b)
+    _, dwa = IF.backward(dev(x), a, dev(w), groups=4)
+    _, dwb = IF.backward(dev(x), a, dev(w[:, :2]), groups=4)
+    assert torch.equal(dwa[:, :2], dwb) and torch.all(dwa[:, 2:] == 0)
+
+
+def test_masked_weight_entries_are_ignored(IF):
+    """the diagonal tap and the centre-tap upper triangle never influence the result
+    (solve_mc.py:104-108; the CUDA kernels skip k_c == c, .cu:58-60)."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, 6, 8, 8)).astype(np.float32)
+    w = make_weight(rng, 6, 6, 3, 3, 0.05)
+    w2 = w.copy()
+    for c in range(6):
+        w2[c, c:, -1, -1] = rng.standard_normal(6 - c) * 100
+    assert torch.equal(IF.inverse(dev(x), dev(w)), IF.inverse(dev(x), dev(w2)))
+    assert torch.equal(IF.conv(dev(x), dev(w)), IF.conv(dev(x), dev(w2)))
+
+
+def test_empty_batch(IF):
+    w = dev(make_weight(np.random.default_rng(0), 4, 4, 3, 3))
+    x = torch.zeros((0, 4, 5, 5), device="cuda")
+    assert IF.inverse(x, w).shape == (0, 4, 5, 5)
+    assert IF.conv(x, w).shape == (0, 4, 5, 5)
+    dx, dw = IF.backward(x, x, w)
+    assert dx.shape == (0, 4, 5, 5) and dw.shape == w.shape and torch.all(dw == 0)
+
+
+def test_linearity_and_determinism_at_full_batch(IF):
+    """size-independent properties at a BASELINE-sized batch: L^-1 is linear, dW is
+    bit-reproducible (fixed-order reduction), conv(inverse(x)) == x."""
+    torch.manual_seed(0)
+    B, C, H, W, k = 512, 12, 16, 16, 3
+    w = dev(make_weight(np.random.default_rng(1), C, C, k, k, 0.02))
+    x1 = torch.randn(B, C, H, W, device="cuda")
+    x2 = torch.randn(B, C, H, W, device="cuda")
+    y1, y2 = IF.inverse(x1, w, groups=1), IF.inverse(x2, w, groups=1)
+    y12 = IF.inverse(x1 + 2.0 * x2, w, groups=1)
+    scale = float(y12.abs().max())
+    assert float((y12 - (y1 + 2.0 * y2)).abs().max()) / scale < 1e-5
+    assert float((IF.conv(y1, w, groups=1) - x1).abs().max()) / float(x1.abs().max()) < 1e-5
+    g = torch.randn(B, C, H, W, device="cuda")
+    dx_a, dw_a = IF.backward(g, y1, w, groups=1)
+    dx_b, dw_b = IF.backward(g, y1, w, groups=1)
+    assert torch.equal(dx_a, dx_b) and torch.equal(dw_a, dw_b)
+    # adjoint identity <g, L^-1 x> == <L^-T g, x>
+    lhs = float((g.double() * y1.double()).sum())
+    rhs = float((dx_a.double() * x1.double()).sum())
+    assert abs(lhs - rhs) / max(abs(lhs), 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(512, 3, 64, 64, 3, 1), (256, 12, 32, 32, 3, 1), (64, 48, 16, 16, 3, 4),
+                                   (512, 1, 28, 28, 3, 1)], ids=str)
+def test_round_trip_at_sweep_sizes(IF, shape):
+    """encode -> decode round trip at microbenchmark-sweep sizes (too big for the CPU oracle)."""
+    B, C, H, W, k, groups = shape
+    torch.manual_seed(1)
+    w = dev(make_weight(np.random.default_rng(4), C, C, k, k, 0.01))
+    x = torch.randn(B, C, H, W, device="cuda")
+    y = IF.inverse(x, w, groups=groups)
+    assert float((IF.conv(y, w, groups=groups) - x).abs().max()) / float(x.abs().max()) < 1e-5
+    # a slice of the batch against the oracle
+    y_ref = oracle.inverse(x[:2].cpu().numpy().astype(np.float64), w.cpu().numpy().astype(np.float64), groups)
+    assert oracle.max_rel_err(y[:2].cpu().numpy(), y_ref) < TOL
+
+
+def test_autograd_function_matches_oracle(IF):
+    from inverse_flow_b200.layers import inv_conv_4d
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((4, 8, 7, 7)).astype(np.float32)
+    g = rng.standard_normal((4, 8, 7, 7)).astype(np.float32)
+    w = make_weight(rng, 8, 8, 3, 3, 0.05)
+    for groups in (1, 4):
+        xt = dev(x).requires_grad_(True)
+        wt = dev(w).requires_grad_(True)
+        y = inv_conv_4d(xt, wt, groups)
+        y.backward(dev(g))
+        y_ref = oracle.inverse(x.astype(np.float64), w.astype(np.float64), groups)
+        dx_ref, dw_ref = oracle.backward(g.astype(np.float64), y_ref, w.astype(np.float64), groups)
+        assert oracle.max_rel_err(y.detach().cpu().numpy(), y_ref) < TOL
+        assert oracle.max_rel_err(xt.grad.cpu().numpy(), dx_ref) < TOL
+        assert oracle.max_rel_err(wt.grad.cpu().numpy(), dw_ref) < TOL
+
+
+def test_layers_round_trip_like_the_reference_test():
+    """tests/inf/test_layers.py:19-36, 182-190: reverse(forward(x)) == x, atol 1e-3."""
+    from inverse_flow_b200.layers import Inv_FlowUnit, inv_flow_no_pad, inv_flow_with_pad
+    torch.manual_seed(0)
+    input_size = (1, 4, 5, 5)
+    mods = [inv_flow_no_pad(4, 4, (3, 3)), inv_flow_with_pad(4, 4, (3, 3), order='TL')]
+    mods += [inv_flow_with_pad(8, 8, (3, 3), order=o, groups=1) for o in ('TR', 'BL', 'BR')]
+    mods += [Inv_FlowUnit(8, 8, (3, 3)), inv_flow_no_pad(12, 12, (2, 2), groups=1)]
+    for m in mods:
+        m = m.to('cuda')
+        C = m.conv_tl.in_channels if isinstance(m, Inv_FlowUnit) else m.in_channels
+        x = torch.randn(3, C, *input_size[2:], device='cuda')
+        out = m(x)
+        fwd, logdet = out
+        assert logdet == 0.0
+        rev = m.reverse(fwd.detach())
+        np.testing.assert_allclose(rev.cpu().numpy(), x.cpu().numpy(), atol=1e-3)
+
+
+def test_layer_order_matches_flipped_oracle():
+    from inverse_flow_b200.layers import inv_flow_with_pad
+    torch.manual_seed(0)
+    m = inv_flow_with_pad(4, 4, (3, 3), order='BR', groups=1).to('cuda')
+    x = torch.randn(2, 4, 6, 6, device='cuda')
+    y, _ = m(x)
+    w = m.weight_fwd.detach().cpu().numpy().astype(np.float64)
+    xf = x.cpu().numpy().astype(np.float64)[:, :, ::-1, ::-1]
+    y_ref = oracle.inverse(np.ascontiguousarray(xf), w, 1)[:, :, ::-1, ::-1]
+    assert oracle.max_rel_err(y.detach().cpu().numpy(), y_ref) < TOL
+
+
+def test_reference_module_call_style():
+    """inv_conv.py:48-56, 262-267: caller-allocated zero output, result is list[0]."""
+    from inverse_flow_b200 import inv_conv_with_bp
+    rng = np.random.default_rng(9)
+    x = dev(rng.standard_normal((2, 4, 5, 5)))
+    w = dev(make_weight(rng, 4, 4, 3, 3))
+    out = x * 0.0
+    z = inv_conv_with_bp.inverse(x, w, out)
+    assert z[0].data_ptr() == out.data_ptr()
+    back = inv_conv_with_bp.forward(z[0], w, torch.zeros_like(x))
+    np.testing.assert_allclose(back[0].cpu().numpy(), x.cpu().numpy(), atol=1e-5)
+    with pytest.raises(RuntimeError):
+        inv_conv_with_bp.inverse(x.transpose(2, 3), w, out)        # CHECK_CONTIGUOUS
+
+
+def test_runs_on_the_callers_stream_and_in_a_graph(IF):
+    """asynchronous on the current stream, capturable in a CUDA graph (no device syncs)."""
+    rng = np.random.default_rng(10)
+    x = dev(rng.standard_normal((8, 12, 16, 16)))
+    w = dev(make_weight(rng, 12, 12, 3, 3, 0.02))
+    ref = IF.inverse(x, w, groups=1)
+    prepared = IF.Prepared(w, 1)
+    out = torch.empty_like(x)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        IF.inverse(x, w, out=out, prepared=prepared)          # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    out.zero_()
+    with torch.cuda.graph(graph):
+        IF.inverse(x, w, out=out, prepared=prepared)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
