@@ -195,10 +195,10 @@ void ifk_oracle_bwd_weight_##SUFFIX(const T *dx, const T *y, T *dw, int B, int C
 {                                                                                           \
     const int Cg = C / groups;                                                              \
     memset(dw, 0, sizeof(T) * (size_t)C * Cw * KH * KW);                                    \
-    _Pragma("omp parallel for schedule(static) num_threads(threads)")                       \
+    _Pragma("omp parallel for collapse(2) schedule(static) num_threads(threads)")           \
     for (int c = 0; c < C; c++) {                                                           \
-        const int base = (c / Cg) * Cg, cl = c - base;                                      \
-        for (int kc = 0; kc < Cg; kc++)                                                     \
+        for (int kc = 0; kc < Cg; kc++) {                                                   \
+            const int base = (c / Cg) * Cg, cl = c - base;                                  \
             for (int qh = 0; qh < KH; qh++)                                                 \
                 for (int qw = 0; qw < KW; qw++) {                                           \
                     if (qh == 0 && qw == 0 && kc >= cl) continue;                           \
@@ -211,6 +211,7 @@ void ifk_oracle_bwd_weight_##SUFFIX(const T *dx, const T *y, T *dw, int B, int C
                                                       w - qw)];                             \
                     dw[IDX4(Cw, KH, KW, c, kc, KH - 1 - qh, KW - 1 - qw)] = (T)(-acc);      \
                 }                                                                           \
+        }                                                                                   \
     }                                                                                       \
 }                                                                                           \
                                                                                             \

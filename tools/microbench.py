@@ -37,34 +37,39 @@ def make_weight(C, k, gen):
     return w
 
 
-def time_op(fn, iters, flush=None):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    if flush is None:
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(iters):
+def time_op(fn, iters, flush=None, reps=20):
+    """microseconds per call: `reps` calls captured in one CUDA graph (no Python / launch
+    overhead between them), replayed `iters` times, CUDA events around each replay."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
             fn()
-        e.record()
-        torch.cuda.synchronize()
-        return s.elapsed_time(e) * 1e3 / iters
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            fn()
+    graph.replay()
+    torch.cuda.synchronize()
     tot = 0.0
     for _ in range(iters):
-        flush.zero_()
+        if flush is not None:
+            flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        fn()
+        graph.replay()
         e.record()
         torch.cuda.synchronize()
         tot += s.elapsed_time(e) * 1e3
-    return tot / iters
+    return tot / iters / reps
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="model")
-    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default=None)
     ap.add_argument("--flush", action="store_true", help="flush L2 between iterations (cold)")
     args = ap.parse_args()
