@@ -22,7 +22,8 @@ int make_geometry(const ifk_problem *p, Geometry *g)
         return IFK_ERR_UNSUPPORTED;
     g->KD = (int)kd;
     g->KDP = round_up(g->KD, 4);
-    if ((size_t)g->Cg * g->Cg * sizeof(float) > (size_t)kMaxSmemBytes) return IFK_ERR_UNSUPPORTED;
+    if ((size_t)3 * g->Cg * (g->Cg + 1) * sizeof(float) > (size_t)kMaxSmemBytes)
+        return IFK_ERR_UNSUPPORTED;                      // ifk_prepare stages three Cg x Cg matrices
     return IFK_OK;
 }
 
@@ -118,6 +119,10 @@ int ifk_backward_f32(const ifk_problem *p, const float *grad, const float *y, co
     if (st != IFK_OK) return st;
     return ifk_bwd_weight_f32(p, dx, y, dw, workspace, stream);
 }
+
+// Tuning aid, deliberately not in ifk.h: device buffer of >= 16 int64 that CTA (0,0) of the
+// next solve launches fills with clock64() stamps of its phases (nullptr switches it off).
+void ifk_debug_set_probe(long long *device_buffer) { set_solve_probe(device_buffer); }
 
 int ifk_describe_solve(const ifk_problem *p, char *buf, size_t buflen)
 {

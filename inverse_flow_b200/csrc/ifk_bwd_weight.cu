@@ -4,27 +4,32 @@
 // a serial H*W raster loop inside each of <= K*4*C threads, 2*(2K-1)*C/4 launches) by a
 // batch-summed correlation of the input gradient with the saved output.
 //
-// Stage 1  bwd_weight_partial_kernel: CTA = (batch chunk, group, slab of work items); an
-//          item is one tap q with a 4x4 tile of (c, kc) and is owned by ONE WARP whose lanes
-//          stride over the pixels (conflict-free shared-memory reads), accumulators live in
-//          registers across the whole chunk, one shuffle reduction at the end.
+// Stage 1  bwd_weight_partial_kernel: CTA = (batch chunk, group, slab of work items).  A work
+//          item is one tap q with a 4x4 tile of (c, kc); a warp owns up to NI consecutive items
+//          and keeps their 16*NI accumulators in registers across the whole chunk; its lanes
+//          stride over the pixels, so every shared-memory read is a conflict-free row of 32
+//          distinct words.  The chunk's images (dX and y, both contiguous NCHW group slices)
+//          arrive by TMA bulk copies, double buffered: image n+1 lands while image n is
+//          consumed.  One shuffle reduction per accumulator at the very end.
 // Stage 2  bwd_weight_reduce_kernel: sums the per-chunk partials in chunk order (fixed order,
 //          no atomics -> bit-reproducible), negates, masks, scatters into the weight layout.
-#include "ifk_internal.cuh"
+#include "ifk_solve_kernel.cuh"   // TMA / mbarrier primitives
 
 namespace ifk {
 
-constexpr int kTile = 4;            // (c, kc) register tile edge
-constexpr int kItemsPerCta = 16;    // warps per CTA
+constexpr int kTile = 4;         // (c, kc) register tile edge
+constexpr int kWarps = 16;       // warps per CTA
+constexpr int kNI = 4;           // max items per warp (16 accumulators each)
 
 struct BwdWeightPlan {
     int nt;            // tiles per channel axis
     int items;         // K * nt * nt
-    int nz;            // item slabs
+    int per_warp;      // items per warp (<= kNI)
+    int nz;            // item slabs (grid.z)
     int nchunks;       // batch chunks (== partial buffers)
     int per_chunk;     // images per chunk
-    bool staged;       // images resident in shared memory
-    int HP, WP, YS;    // halo-padded geometry of the staged y image, its channel stride
+    int nbuf;          // 2: double buffered, 1: single, 0: images read from global memory
+    int XN;            // floats per staged image (16-byte multiple)
     size_t smem_bytes;
 };
 
@@ -33,18 +38,20 @@ static BwdWeightPlan make_plan(const Geometry &g)
     BwdWeightPlan pl{};
     pl.nt = (g.Cg + kTile - 1) / kTile;
     pl.items = g.K * pl.nt * pl.nt;
-    pl.nz = (pl.items + kItemsPerCta - 1) / kItemsPerCta;
-    int want = (2 * kNumSM + g.groups * pl.nz - 1) / (g.groups * pl.nz);
+    pl.per_warp = (pl.items + kWarps - 1) / kWarps;
+    if (pl.per_warp > kNI) pl.per_warp = kNI;
+    const int per_cta = kWarps * pl.per_warp;
+    pl.nz = (pl.items + per_cta - 1) / per_cta;
+    int want = (kNumSM + g.groups * pl.nz - 1) / (g.groups * pl.nz);
     if (want < 1) want = 1;
     if (want > g.B) want = g.B > 0 ? g.B : 1;
     pl.per_chunk = g.B > 0 ? (g.B + want - 1) / want : 1;
     pl.nchunks = g.B > 0 ? (g.B + pl.per_chunk - 1) / pl.per_chunk : 1;
-    pl.HP = g.H + g.KH - 1;
-    pl.WP = g.W + g.KW - 1;
-    pl.YS = pl.HP * pl.WP;
-    pl.smem_bytes = (size_t)g.Cg * ((size_t)g.H * g.W + pl.YS) * sizeof(float);
-    pl.staged = pl.smem_bytes <= (size_t)kMaxSmemBytes;
-    if (!pl.staged) pl.smem_bytes = 0;
+    pl.XN = round_up(round_up(g.Cg, kTile) * g.H * g.W, 4);   // channels padded to the tile: no clamps
+    const size_t one = (size_t)2 * pl.XN * sizeof(float);          // dX + y of one image
+    pl.nbuf = 2 * one + 64 <= (size_t)kMaxSmemBytes ? 2 : (one + 64 <= (size_t)kMaxSmemBytes ? 1 : 0);
+    if (pl.per_chunk == 1 && pl.nbuf == 2) pl.nbuf = 1;
+    pl.smem_bytes = pl.nbuf ? 64 + pl.nbuf * one : 0;
     return pl;
 }
 
@@ -54,111 +61,153 @@ size_t bwd_weight_workspace_bytes(const Geometry &g)
     return (size_t)pl.nchunks * g.C * g.Cg * g.K * sizeof(float);
 }
 
-template <bool STAGED>
-__global__ void __launch_bounds__(kItemsPerCta * 32)
-bwd_weight_partial_kernel(const float *__restrict__ dx, const float *__restrict__ y,
-                          float *__restrict__ partial, int B, int C, int H, int W, int KH, int KW,
-                          int Cg, int nt, int items, int per_chunk, int WP, int YS)
+struct BwdWeightParams {
+    const float *dx, *y;
+    float *partial;
+    int B, C, H, W, KH, KW, Cg, nt, items, per_warp, per_chunk, nbuf, XN, bulk;
+};
+
+template <int NI>
+__global__ void __launch_bounds__(kWarps * 32)
+bwd_weight_partial_kernel(const BwdWeightParams p)
 {
-    extern __shared__ __align__(16) float smem[];
-    const int HW = H * W, K = KH * KW;
+    extern __shared__ __align__(128) float smem[];
+    const int H = p.H, W = p.W, HW = p.H * p.W, K = p.KH * p.KW, Cg = p.Cg, nt = p.nt;
     const int chunk = blockIdx.x, G = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.z * kItemsPerCta + warp;
-    const bool live = item < items;
-    const int t = live ? item / (nt * nt) : 0;
-    const int rem = live ? item - t * nt * nt : 0;
-    const int c0 = (rem / nt) * kTile, k0 = (rem % nt) * kTile;
-    const int qh = t / KW, qw = t - qh * KW;
-    const int halo = (KH - 1) * WP + (KW - 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);          // [2] one per buffer
+    float *buf0 = smem + 16;                                      // buffer b: dX at b*2*XN, y behind it
 
-    float *dxs = smem;                 // [Cg][HW]
-    float *ys = smem + Cg * HW;        // [Cg][YS], zero halo on top/left
-    if (STAGED) {
-        for (int i = threadIdx.x; i < Cg * YS; i += blockDim.x) ys[i] = 0.f;
+    // this warp's items: consecutive, so they mostly share the c tile
+    const int item0 = (blockIdx.z * kWarps + warp) * p.per_warp;
+    int aoff[NI], voff[NI], qhw[NI];
+    bool live[NI];
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+        const int it = item0 + j;
+        live[j] = j < p.per_warp && it < p.items;
+        const int itc = live[j] ? it : 0;
+        const int t = itc % K, tile = itc / K;
+        const int qh = t / p.KW, qw = t - qh * p.KW;
+        aoff[j] = (tile / nt) * kTile * HW;                       // first dX channel of the tile
+        voff[j] = (tile % nt) * kTile * HW - (qh * W + qw);       // first y channel, shifted by the tap
+        qhw[j] = (qh << 16) | qw;
     }
+    float acc[NI][kTile][kTile];
+#pragma unroll
+    for (int j = 0; j < NI; j++)
+#pragma unroll
+        for (int a = 0; a < kTile; a++)
+#pragma unroll
+            for (int b = 0; b < kTile; b++) acc[j][a][b] = 0.f;
 
-    float acc[kTile][kTile];
-#pragma unroll
-    for (int i = 0; i < kTile; i++)
-#pragma unroll
-        for (int j = 0; j < kTile; j++) acc[i][j] = 0.f;
+    const int b_begin = chunk * p.per_chunk;
+    const int b_end = b_begin + p.per_chunk < p.B ? b_begin + p.per_chunk : p.B;
+    const size_t img_stride = (size_t)p.C * HW;
+    const float *dx0 = p.dx + (size_t)G * Cg * HW, *y0 = p.y + (size_t)G * Cg * HW;
+    const uint32_t img_bytes = (uint32_t)(Cg * HW) * 4u;
+    const bool staged = p.nbuf > 0, bulk = staged && p.bulk;
 
-    // channel indices clamped into the group; out-of-range tile rows are dropped at the end
-    int cidx[kTile], kidx[kTile];
-#pragma unroll
-    for (int i = 0; i < kTile; i++) {
-        cidx[i] = c0 + i < Cg ? c0 + i : Cg - 1;
-        kidx[i] = k0 + i < Cg ? k0 + i : Cg - 1;
+    if (bulk && tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_expect_tx(&bars[0], 2 * img_bytes);
+        bulk_load(buf0, dx0 + (size_t)b_begin * img_stride, img_bytes, &bars[0]);
+        bulk_load(buf0 + p.XN, y0 + (size_t)b_begin * img_stride, img_bytes, &bars[0]);
     }
+    if (staged) {       // channels padded up to the tile are zero for good (bulk copies never touch them)
+        for (int bsel = 0; bsel < 2 * p.nbuf; bsel++)
+            for (int i = Cg * HW + tid; i < p.XN; i += blockDim.x) buf0[(size_t)bsel * p.XN + i] = 0.f;
+    }
+    __syncthreads();
+    uint32_t parity0 = 0u, parity1 = 0u;
 
-    const int b_begin = chunk * per_chunk;
-    const int b_end = b_begin + per_chunk < B ? b_begin + per_chunk : B;
     for (int b = b_begin; b < b_end; b++) {
-        const size_t gbase = ((size_t)b * C + (size_t)G * Cg) * HW;
-        if (STAGED) {
-            __syncthreads();           // previous image fully consumed
-            for (int i = threadIdx.x; i < Cg * HW; i += blockDim.x) {
-                const int ci = i / HW, r = i - ci * HW;
-                const int h = r / W, w = r - h * W;
-                dxs[i] = __ldg(dx + gbase + i);
-                ys[ci * YS + h * WP + w + halo] = __ldg(y + gbase + i);
+        const int cur = p.nbuf == 2 ? (b - b_begin) & 1 : 0;
+        const float *dxs, *ys;
+        if (staged) {
+            float *bufc = buf0 + (size_t)cur * 2 * p.XN;
+            if (bulk) {
+                if (p.nbuf == 2 && b + 1 < b_end && tid == 0) {          // prefetch into the other buffer
+                    float *bufn = buf0 + (size_t)(cur ^ 1) * 2 * p.XN;   // (its readers passed the barrier below)
+                    mbar_expect_tx(&bars[cur ^ 1], 2 * img_bytes);
+                    bulk_load(bufn, dx0 + (size_t)(b + 1) * img_stride, img_bytes, &bars[cur ^ 1]);
+                    bulk_load(bufn + p.XN, y0 + (size_t)(b + 1) * img_stride, img_bytes, &bars[cur ^ 1]);
+                }
+                mbar_wait(&bars[cur], cur ? parity1 : parity0);
+                if (cur) parity1 ^= 1u; else parity0 ^= 1u;
+            } else {
+                __syncthreads();
+                const float *sd = dx0 + (size_t)b * img_stride, *sy = y0 + (size_t)b * img_stride;
+                for (int i = tid; i < Cg * HW; i += blockDim.x) {
+                    bufc[i] = __ldg(sd + i);
+                    bufc[p.XN + i] = __ldg(sy + i);
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            if (live) {
-                for (int r = lane; r < HW; r += 32) {
-                    const int h = r / W, w = r - h * W;
-                    const int yo = h * WP + w + halo - qh * WP - qw;
-                    float a[kTile], v[kTile];
+            dxs = bufc;
+            ys = bufc + p.XN;
+        } else {
+            dxs = dx0 + (size_t)b * img_stride;
+            ys = y0 + (size_t)b * img_stride;
+        }
+
+        for (int r = lane; r < HW; r += 32) {
+            const int h = r / W, w = r - h * W;
+#pragma unroll
+            for (int j = 0; j < NI; j++) {
+                if (!live[j] || h < (qhw[j] >> 16) || w < (qhw[j] & 0xffff)) continue;
+                float a[kTile], v[kTile];
+                if (staged) {
 #pragma unroll
                     for (int i = 0; i < kTile; i++) {
-                        a[i] = dxs[cidx[i] * HW + r];
-                        v[i] = ys[kidx[i] * YS + yo];
+                        a[i] = dxs[aoff[j] + i * HW + r];
+                        v[i] = ys[voff[j] + i * HW + r];
                     }
+                } else {
+                    const int cbase = aoff[j] / HW, kbase = (voff[j] + (qhw[j] >> 16) * W + (qhw[j] & 0xffff)) / HW;
 #pragma unroll
-                    for (int i = 0; i < kTile; i++)
-#pragma unroll
-                        for (int j = 0; j < kTile; j++) acc[i][j] = fmaf(a[i], v[j], acc[i][j]);
-                }
-            }
-        } else if (live) {
-            const float *dxb = dx + gbase, *yb = y + gbase;
-            for (int r = lane; r < HW; r += 32) {
-                const int h = r / W, w = r - h * W;
-                if (h < qh || w < qw) continue;
-                const int rn = r - qh * W - qw;
-                float a[kTile], v[kTile];
-#pragma unroll
-                for (int i = 0; i < kTile; i++) {
-                    a[i] = __ldg(dxb + (size_t)cidx[i] * HW + r);
-                    v[i] = __ldg(yb + (size_t)kidx[i] * HW + rn);
+                    for (int i = 0; i < kTile; i++) {
+                        const int ci = cbase + i < Cg ? i : Cg - 1 - cbase;   // clamped; dropped at the end
+                        const int ki = kbase + i < Cg ? i : Cg - 1 - kbase;
+                        a[i] = __ldg(dxs + aoff[j] + ci * HW + r);
+                        v[i] = __ldg(ys + voff[j] + ki * HW + r);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < kTile; i++)
 #pragma unroll
-                    for (int j = 0; j < kTile; j++) acc[i][j] = fmaf(a[i], v[j], acc[i][j]);
+                    for (int k = 0; k < kTile; k++) acc[j][i][k] = fmaf(a[i], v[k], acc[j][i][k]);
+            }
+        }
+        if (bulk && p.nbuf == 2) __syncthreads();      // everyone is done with `cur` before it is refilled
+        if (bulk && p.nbuf == 1 && b + 1 < b_end) {
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&bars[0], 2 * img_bytes);
+                bulk_load(buf0, dx0 + (size_t)(b + 1) * img_stride, img_bytes, &bars[0]);
+                bulk_load(buf0 + p.XN, y0 + (size_t)(b + 1) * img_stride, img_bytes, &bars[0]);
             }
         }
     }
 
-    if (!live) return;
+    float *out = p.partial + ((size_t)chunk * p.C + (size_t)G * Cg) * Cg * K;   // [c][kc][t]
 #pragma unroll
-    for (int i = 0; i < kTile; i++)
-#pragma unroll
-        for (int j = 0; j < kTile; j++) {
-            float s = acc[i][j];
-#pragma unroll
-            for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-            acc[i][j] = s;
-        }
-    if (lane == 0) {
-        float *out = partial + ((size_t)chunk * C + (size_t)G * Cg) * Cg * K;   // [c][kc][t]
+    for (int j = 0; j < NI; j++) {
+        if (!live[j]) continue;                       // warp-uniform
+        const int it = item0 + j;
+        const int t = it % K, tile = it / K;
+        const int c0 = (tile / nt) * kTile, k0 = (tile % nt) * kTile;
 #pragma unroll
         for (int i = 0; i < kTile; i++)
 #pragma unroll
-            for (int j = 0; j < kTile; j++)
-                if (c0 + i < Cg && k0 + j < Cg)
-                    out[((size_t)(c0 + i) * Cg + (k0 + j)) * K + t] = acc[i][j];
+            for (int k = 0; k < kTile; k++) {
+                float s = acc[j][i][k];
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+                if (lane == 0 && c0 + i < Cg && k0 + k < Cg)
+                    out[((size_t)(c0 + i) * Cg + (k0 + k)) * K + t] = s;
+            }
     }
 }
 
@@ -179,8 +228,16 @@ bwd_weight_reduce_kernel(const float *__restrict__ partial, float *__restrict__ 
         float s = 0.f;
         if (kc < Cg && !(qh == 0 && qw == 0 && kc >= cl)) {
             const float *src = partial + ((size_t)c * Cg + kc) * K + (qh * KW + qw);
-            for (int n = 0; n < nchunks; n++) s += src[n * chunk_stride];
-            s = -s;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // fixed association: still deterministic
+            int n = 0;
+            for (; n + 3 < nchunks; n += 4) {
+                s0 += __ldg(src + (size_t)n * chunk_stride);
+                s1 += __ldg(src + (size_t)(n + 1) * chunk_stride);
+                s2 += __ldg(src + (size_t)(n + 2) * chunk_stride);
+                s3 += __ldg(src + (size_t)(n + 3) * chunk_stride);
+            }
+            for (; n < nchunks; n++) s0 += __ldg(src + (size_t)n * chunk_stride);
+            s = -((s0 + s1) + (s2 + s3));
         }
         dw[e] = s;
     }
@@ -193,22 +250,28 @@ int launch_bwd_weight(const Geometry &g, const float *dx, const float *y, float 
     float *partial = (float *)workspace;
     const int total = g.C * g.Cw * g.K;
     if (g.B > 0) {
+        BwdWeightParams p{};
+        p.dx = dx; p.y = y; p.partial = partial;
+        p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW; p.Cg = g.Cg;
+        p.nt = pl.nt; p.items = pl.items; p.per_warp = pl.per_warp; p.per_chunk = pl.per_chunk;
+        p.nbuf = pl.nbuf; p.XN = pl.XN;
+        const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
+        p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) ? 1 : 0;
+        if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
         dim3 grid(pl.nchunks, g.groups, pl.nz);
-        const int threads = kItemsPerCta * 32;
-        if (pl.staged) {
-            auto kern = bwd_weight_partial_kernel<true>;
-            if (pl.smem_bytes > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)pl.smem_bytes);
-                if (e != cudaSuccess) return (int)e;
-            }
-            kern<<<grid, threads, pl.smem_bytes, s>>>(dx, y, partial, g.B, g.C, g.H, g.W, g.KH, g.KW,
-                                                      g.Cg, pl.nt, pl.items, pl.per_chunk, pl.WP, pl.YS);
-        } else {
-            bwd_weight_partial_kernel<false><<<grid, threads, 0, s>>>(
-                dx, y, partial, g.B, g.C, g.H, g.W, g.KH, g.KW, g.Cg, pl.nt, pl.items, pl.per_chunk,
-                pl.WP, pl.YS);
+        void (*kern)(const BwdWeightParams) = bwd_weight_partial_kernel<4>;
+        switch (pl.per_warp) {
+            case 1: kern = bwd_weight_partial_kernel<1>; break;
+            case 2: kern = bwd_weight_partial_kernel<2>; break;
+            case 3: kern = bwd_weight_partial_kernel<3>; break;
+            default: break;
         }
+        if (pl.smem_bytes > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)pl.smem_bytes);
+            if (e != cudaSuccess) return (int)e;
+        }
+        kern<<<grid, kWarps * 32, pl.smem_bytes, s>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }

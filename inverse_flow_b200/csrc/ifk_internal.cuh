@@ -34,6 +34,7 @@ size_t bwd_weight_workspace_bytes(const Geometry &g);
 int launch_bwd_weight(const Geometry &g, const float *dx, const float *y, float *dw,
                       void *workspace, cudaStream_t s);
 int describe_solve(const Geometry &g, char *buf, size_t buflen);
+void set_solve_probe(long long *device_buffer);
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 

@@ -1,0 +1,428 @@
+// Shared-memory resident wavefront solve kernel (template) and its parameter block.
+// Included by the per-vector-width translation units ifk_solve_v{1,2,4}.cu.
+//
+// Replaces the reference's per-diagonal launch loop
+// (inf/utils/inv_conv_cuda/inv_conv_with_bp_kernel_general.cu:72-129: (H+W-1)*C/4 launches,
+// each followed by cudaDeviceSynchronize, one thread per (batch, group, pixel), dependent
+// global read-modify-writes) by ONE launch.  Per image of the CTA's batch stripe:
+//   1. the group's image (contiguous in NCHW) lands in `xbuf` by one TMA bulk copy
+//      (cp.async.bulk + mbarrier); the next image of the stripe is prefetched as soon as
+//      xbuf has been consumed;
+//   2. pre-pass, no dependencies: z = T x for every pixel into `zbuf` (T = (I + A0)^-1 is
+//      tap 0 of the prepared kernel; skipped when Cg == 1);
+//   3. wavefront: thread -> (row slot, ct, ks) walks its image row, one pixel per
+//      anti-diagonal.  `ct` = tile of CC output channels, `ks` = slice of the (K-1)*Cg
+//      neighbour reduction.  y lives in `ybuf` as [row][col][channel] with a zero halo, so a
+//      neighbour pixel's channels are VEC-wide contiguous vectors: NV vector loads per thread
+//      per pixel, weights of the slice in registers for the whole stripe, partial sums
+//      combined by full-warp shuffles, the ks == 0 lane adds z and writes y into `ybuf`
+//      (for later diagonals) and in place into `zbuf`; one block barrier per diagonal;
+//   4. `zbuf` returns to global memory by one TMA bulk store.
+// The adjoint solve (reverse) is the same walk in reflected coordinates: only the index into
+// the contiguous buffers is mirrored.
+#pragma once
+#include "ifk_internal.cuh"
+
+namespace ifk {
+
+struct SolveParams {
+    const float *in;
+    float *out;
+    const float *prep;  // prepared weights of this direction: [group][co][KDP]
+    int B, C, H, W, KH, KW, Cg, KD, KDP;
+    int WP;             // halo-padded width  (W + KW - 1)
+    int PS;             // pixel stride of ybuf in floats (channels rounded up, conflict padded)
+    int YN;             // floats in ybuf = (H + KH - 1) * WP * PS
+    int XN;             // floats per contiguous image buffer (Cg*H*W rounded up to 4)
+    int CgV;            // channel vectors per pixel = ceil(Cg / VEC)
+    int NVT;            // (K - 1) * CgV : vector entries of one output row's reduction
+    int CgP4;           // Cg rounded up to 4 (row stride of the transposed T in smem)
+    int NS, NCT, nslots, iters;
+    int reverse;
+    int bulk;           // image size / pointers allow TMA bulk copies (16-byte granularity)
+    long long *probe;   // tuning aid: clock64() stamps of CTA (0,0) thread 0, or nullptr
+};
+
+// ---- TMA bulk copy / mbarrier primitives (PTX; SASS: UBLKCP, SYNCS) -----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "IFK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra IFK_DONE_%=;\n\t"
+        "bra IFK_WAIT_%=;\n\t"
+        "IFK_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_proxy()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- vector loads from shared memory by 32-bit shared-space address -------------------------
+template <int VEC>
+__device__ __forceinline__ void lds_vec(float *v, uint32_t addr);
+template <>
+__device__ __forceinline__ void lds_vec<1>(float *v, uint32_t addr)
+{
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr) : "memory");
+}
+template <>
+__device__ __forceinline__ void lds_vec<2>(float *v, uint32_t addr)
+{
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr) : "memory");
+}
+template <>
+__device__ __forceinline__ void lds_vec<4>(float *v, uint32_t addr)
+{
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                 : "r"(addr)
+                 : "memory");
+}
+
+// ---- reduce-scatter of N partial sums over the NS adjacent lanes of a pixel ------------------
+// Recursive halving: at the level with lane mask m every lane keeps one half of its current
+// values and receives the partner's partial sums of that half (N/2 + N/4 + ... shuffles in
+// total, against N*log2(NS) for a butterfly) and the finished channels end up spread over the
+// lanes, which then write them.  The value counts per level are compile-time; NS is a runtime
+// (warp-uniform) parameter that only decides how many levels run.  After the last level lane
+// `ks` holds the complete sums of channels [off, off + size) of its tile in acc[0 .. size),
+// (off, size) = rs_owner(CC, NS, ks).
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+template <int N, int LEVELS>
+struct Rs {
+    // zv: z of the channels this lane finishes; ya/za: shared addresses of their y / in-place slots
+    __device__ __forceinline__ static void run(float *acc, const float *zv, int ks, int m, int own_size,
+                                               bool active, uint32_t ya, uint32_t za, uint32_t zstride)
+    {
+        if (m == 0 || LEVELS == 0) {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                if (active && i < own_size) {
+                    const float yv = acc[i] + zv[i];
+                    sts_f32(ya + 4u * i, yv);
+                    sts_f32(za + zstride * i, yv);
+                }
+            return;
+        }
+        constexpr int HALF = (N + 1) / 2;
+        const bool hi = (ks & m) != 0;
+#pragma unroll
+        for (int i = 0; i < HALF; i++) {
+            const float lo_v = acc[i];
+            const float hi_v = (i + HALF < N) ? acc[i + HALF] : 0.f;
+            const float send = hi ? lo_v : hi_v;
+            const float keep = hi ? hi_v : lo_v;
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+        Rs<HALF, (LEVELS > 0 ? LEVELS - 1 : 0)>::run(acc, zv, ks, m >> 1, own_size, active, ya, za, zstride);
+    }
+};
+
+__device__ __forceinline__ void rs_owner(int n, int m, int ks, int *off, int *size)
+{
+    int o = 0, sz = n;
+    for (; m > 1; m >>= 1) {
+        const int half = (n + 1) / 2;
+        if (ks & (m / 2)) { o += half; sz = sz - half > 0 ? sz - half : 0; }
+        else              { sz = sz < half ? sz : half; }
+        n = half;
+    }
+    *off = o;
+    *size = sz;
+}
+
+template <int CC, int NV, int VEC>
+constexpr int solve_max_threads()
+{
+    // registers: CC*NV*VEC weights + NV*VEC loaded values + NV offsets + CC sums + ~48 of bookkeeping
+    int regs = CC * NV * VEC + NV * VEC + NV + 2 * CC + 48;
+    if (regs > 255) regs = 255;
+    int t = (65536 / regs) / 32 * 32;
+    return t > 1024 ? 1024 : t;
+}
+
+#define IFK_PROBE(i) do { if (p.probe && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.probe[i] = clock64(); } while (0)
+
+template <int CC, int NV, int VEC>
+__global__ void __launch_bounds__(solve_max_threads<CC, NV, VEC>())
+solve_smem_kernel(const SolveParams p)
+{
+    IFK_PROBE(0);
+    extern __shared__ __align__(128) float smem[];
+    const int Cg = p.Cg, WP = p.WP, PS = p.PS, H = p.H, W = p.W, HW = p.H * p.W;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    // shared memory carve-up (every region a multiple of 16 bytes)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);         // 16 bytes reserved
+    int *tbl_off = reinterpret_cast<int *>(smem + 4);           // [NVT] byte offset of a vector entry
+    const int tbl_n = (p.NVT + 3) & ~3;
+    int *tbl_w = tbl_off + tbl_n;                               // [NVT] weight column of its 1st channel
+    float *tT = reinterpret_cast<float *>(tbl_w + tbl_n);       // [Cg][CgP4] transposed T
+    float *xbuf = tT + (Cg > 1 ? Cg * p.CgP4 : 0);              // [Cg][HW] raw input
+    float *zbuf = Cg > 1 ? xbuf + p.XN : xbuf;                  // [Cg][HW] T x, then y in place
+    float *ybuf = zbuf + p.XN;                                  // [HP][WP][PS] y, zero halo top/left
+
+    const int G = blockIdx.y;
+    const float *wg = p.prep + (size_t)G * Cg * p.KDP;
+    const uint32_t img_bytes = (uint32_t)(Cg * HW) * 4u;
+    const size_t img_stride = (size_t)p.C * HW;
+    const float *in0 = p.in + (size_t)G * Cg * HW;
+    float *out0 = p.out + (size_t)G * Cg * HW;
+
+    int b = blockIdx.x;
+    if (p.bulk && tid == 0) {
+        mbar_init(bar, 1);
+        if (b < p.B) {
+            mbar_expect_tx(bar, img_bytes);
+            bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
+        }
+    }
+
+    // tables: where a vector entry lives relative to the pixel, and which weights it meets
+    for (int v = tid; v < p.NVT; v += nthr) {
+        const int t = 1 + v / p.CgV, q = v - (t - 1) * p.CgV;
+        const int qh = t / p.KW, qw = t - qh * p.KW;
+        tbl_off[v] = ((-qh * WP - qw) * PS + q * VEC) * 4;
+        tbl_w[v] = (t - 1) * Cg + q * VEC;
+    }
+    if (Cg > 1)
+        for (int i = tid; i < Cg * p.CgP4; i += nthr) {
+            const int ci = i / p.CgP4, co = i - ci * p.CgP4;
+            tT[i] = co < Cg ? __ldg(wg + (size_t)co * p.KDP + ci) : 0.f;
+        }
+    __syncthreads();        // tables + mbarrier init visible
+    IFK_PROBE(1);
+
+    const int NS = p.NS, NCT = p.NCT;
+    const int ks = tid % NS;
+    const int ct = (tid / NS) % NCT;
+    const int slot = tid / (NS * NCT);
+    const bool worker = slot < p.nslots;
+
+    // this thread's slice of the prepared kernel -> registers, for the whole batch stripe
+    float wreg[CC][NV * VEC];
+    int offs[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const int v = j * NS + ks;
+        const bool valid = worker && v < p.NVT;
+        offs[j] = valid ? tbl_off[v] : 0;          // padding entries: weight 0, reads finite data
+        const int wcol = valid ? tbl_w[v] : 0;
+        const int ci0 = valid ? wcol % Cg : 0;
+#pragma unroll
+        for (int e = 0; e < VEC; e++)
+#pragma unroll
+            for (int cc = 0; cc < CC; cc++) {
+                const int co = ct * CC + cc;
+                wreg[cc][j * VEC + e] = (valid && co < Cg && ci0 + e < Cg)
+                                            ? __ldg(wg + (size_t)co * p.KDP + Cg + wcol + e) : 0.f;
+            }
+    }
+
+    // which of the tile's CC output channels this lane finishes after the reduce-scatter
+    int own_off, own_size;
+    rs_owner(CC, NS, ks, &own_off, &own_size);
+    {
+        const int tile_n = Cg - ct * CC < CC ? Cg - ct * CC : CC;     // channels in this (last) tile
+        own_size = own_off + own_size > tile_n ? (tile_n - own_off > 0 ? tile_n - own_off : 0) : own_size;
+    }
+    const int own_c0 = ct * CC + own_off;
+
+    IFK_PROBE(2);
+    const int ndiag = H + W - 1;
+    const int iters = p.iters, nslots = p.nslots;
+    const uint32_t ybase = smem_u32(ybuf) + (uint32_t)(((p.KH - 1) * WP + (p.KW - 1)) * PS) * 4u;
+    const uint32_t zstride = (uint32_t)HW * 4u;
+    // rows of this thread: slot, slot + nslots, ...; row_ok = how many of them exist
+    const int row_ok = worker && slot < H ? (H - 1 - slot) / nslots + 1 : 0;
+    // pixel (h, w = d - h): ybuf address = ybase + ((h*WP + w)*PS)*4 ; contiguous index rr = h*W + w
+    const uint32_t pix_step = (uint32_t)PS * 4u;                                   // per diagonal
+    const uint32_t pix_row = (uint32_t)(nslots * (WP - 1) * PS) * 4u;              // per row iteration
+    const uint32_t pix0 = ybase + (uint32_t)(slot * (WP - 1) * PS) * 4u;           // d = 0, it = 0
+    const uint32_t z_step = p.reverse ? (uint32_t)(-4) : 4u;
+    const uint32_t z_row = (uint32_t)(nslots * (W - 1)) * z_step;
+    const uint32_t z0 = smem_u32(zbuf) + (uint32_t)(own_c0 * HW) * 4u +
+                        (p.reverse ? (uint32_t)(HW - 1 - slot * (W - 1)) * 4u : (uint32_t)(slot * (W - 1)) * 4u);
+    uint32_t parity = 0;
+    for (; b < p.B; b += gridDim.x) {
+        const int b_next = b + gridDim.x;
+        // ybuf starts from zero for every image: the halo, and the not-yet-written interior that
+        // zero-weight padding entries may touch
+        for (int i = tid * 4; i < p.YN; i += nthr * 4)
+            *reinterpret_cast<float4 *>(ybuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        IFK_PROBE(3);
+        if (p.bulk) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            const float *src = in0 + (size_t)b * img_stride;
+            for (int i = tid; i < Cg * HW; i += nthr) xbuf[i] = __ldg(src + i);
+        }
+        IFK_PROBE(4);
+        if (Cg > 1) {
+            if (tid == 0 && p.bulk) bulk_store_wait_read();     // previous image has left zbuf
+            __syncthreads();
+            // pre-pass z = T x : item (pixel r, 4 output channels), consecutive threads -> pixels
+            const int n4 = p.CgP4 >> 2;
+            for (int i = tid; i < HW * n4; i += nthr) {
+                const int c4 = i / HW, r = i - c4 * HW;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                const float *tp = tT + c4 * 4;
+                for (int ci = 0; ci < Cg; ci++) {
+                    const float xv = xbuf[ci * HW + r];
+                    const float4 t4 = *reinterpret_cast<const float4 *>(tp + ci * p.CgP4);
+                    a0 = fmaf(t4.x, xv, a0);
+                    a1 = fmaf(t4.y, xv, a1);
+                    a2 = fmaf(t4.z, xv, a2);
+                    a3 = fmaf(t4.w, xv, a3);
+                }
+                const int co = c4 * 4;
+                zbuf[co * HW + r] = a0;
+                if (co + 1 < Cg) zbuf[(co + 1) * HW + r] = a1;
+                if (co + 2 < Cg) zbuf[(co + 2) * HW + r] = a2;
+                if (co + 3 < Cg) zbuf[(co + 3) * HW + r] = a3;
+            }
+        }
+        __syncthreads();
+        if (p.bulk && tid == 0 && Cg > 1 && b_next < p.B) {        // prefetch the next image
+            mbar_expect_tx(bar, img_bytes);
+            bulk_load(xbuf, in0 + (size_t)b_next * img_stride, img_bytes, bar);
+        }
+
+        // wavefront.  Row `h0 + it*nslots` of this thread meets diagonal d at column d - h; all
+        // addresses advance by a constant per diagonal, so the loop body is loads, FMAs,
+        // shuffles and stores with a handful of integer instructions.
+        IFK_PROBE(5);
+        uint32_t pix_d = pix0, z_d = z0;
+        for (int d = 0; d < ndiag; d++) {
+            uint32_t pix = pix_d, za = z_d;
+            int col = d - slot;                 // column of this thread's row `it` on diagonal d
+#pragma unroll 1
+            for (int it = 0; it < iters; it++, pix += pix_row, za += z_row, col -= nslots) {
+                const bool active = row_ok > it && (unsigned)col < (unsigned)W;
+                if (!__any_sync(0xffffffffu, active)) continue;        // warp-uniform
+                const uint32_t pa = active ? pix : ybase;              // idle lanes: a legal pixel
+
+                float v[NV * VEC];
+#pragma unroll
+                for (int j = 0; j < NV; j++) lds_vec<VEC>(v + j * VEC, pa + (uint32_t)offs[j]);
+                float zv[CC];
+#pragma unroll
+                for (int i = 0; i < CC; i++) zv[i] = (active && i < own_size) ? lds_f32(za + zstride * i) : 0.f;
+
+                constexpr int NACC = CC >= 4 ? 1 : (CC >= 2 ? 2 : 4);  // independent FMA chains
+                float part[NACC][CC];
+#pragma unroll
+                for (int a = 0; a < NACC; a++)
+#pragma unroll
+                    for (int cc = 0; cc < CC; cc++) part[a][cc] = 0.f;
+#pragma unroll
+                for (int i = 0; i < NV * VEC; i++)
+#pragma unroll
+                    for (int cc = 0; cc < CC; cc++) part[i % NACC][cc] = fmaf(wreg[cc][i], v[i], part[i % NACC][cc]);
+                float acc[CC];
+#pragma unroll
+                for (int cc = 0; cc < CC; cc++) {
+                    acc[cc] = part[0][cc];
+#pragma unroll
+                    for (int a = 1; a < NACC; a++) acc[cc] += part[a][cc];
+                }
+                Rs<CC, 5>::run(acc, zv, ks, NS >> 1, own_size, active, pa + own_c0 * 4u, za, zstride);
+            }
+            pix_d += pix_step;
+            z_d += z_step;
+            if (nthr <= 32) __syncwarp(); else __syncthreads();
+        }
+
+        IFK_PROBE(6);
+        float *dst = out0 + (size_t)b * img_stride;
+        if (p.bulk) {
+            fence_async_proxy();            // generic-proxy writes of zbuf -> visible to the TMA engine
+            __syncthreads();
+            if (tid == 0) {
+                bulk_store(dst, zbuf, img_bytes);
+                if (Cg == 1) {              // zbuf aliases xbuf: reuse only after the store has read it
+                    bulk_store_wait_read();
+                    if (b_next < p.B) {
+                        mbar_expect_tx(bar, img_bytes);
+                        bulk_load(xbuf, in0 + (size_t)b_next * img_stride, img_bytes, bar);
+                    }
+                }
+            }
+        } else {
+            __syncthreads();
+            for (int i = tid; i < Cg * HW; i += nthr) dst[i] = zbuf[i];
+            __syncthreads();
+        }
+    }
+    IFK_PROBE(7);
+    if (p.bulk && tid == 0) bulk_store_wait_read();   // smem must outlive the last store's read
+    IFK_PROBE(8);
+}
+
+// one launcher per vector width (defined in ifk_solve_v{1,2,4}.cu); returns 0, a cudaError_t,
+// or IFK_ERR_UNSUPPORTED when (cc, nv) is not an instantiated variant
+int launch_solve_vec1(int cc, int nv, const SolveParams &p, dim3 grid, int threads, size_t smem, cudaStream_t s);
+int launch_solve_vec2(int cc, int nv, const SolveParams &p, dim3 grid, int threads, size_t smem, cudaStream_t s);
+int launch_solve_vec4(int cc, int nv, const SolveParams &p, dim3 grid, int threads, size_t smem, cudaStream_t s);
+bool solve_variant_exists(int cc, int nv, int vec);
+int solve_variant_max_threads(int cc, int nv, int vec);
+
+template <int CC, int NV, int VEC>
+int launch_solve_variant(const SolveParams &p, dim3 grid, int threads, size_t smem, cudaStream_t s)
+{
+    auto kern = solve_smem_kernel<CC, NV, VEC>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<grid, threads, smem, s>>>(p);
+    return cuda_status(cudaGetLastError());
+}
+
+}  // namespace ifk
