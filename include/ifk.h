@@ -76,9 +76,16 @@ size_t ifk_prepared_floats(const ifk_problem *p);
 int ifk_prepare_f32(const ifk_problem *p, const float *weight, float *prepared,
                     ifk_stream_t stream);
 
+/* The same for `count` weight tensors of one geometry in ONE launch: tensor i starts at
+ * weights + i*weight_stride and is prepared into prepared + i*prepared_stride (strides in
+ * floats).  A model's layers do not depend on activations, so a training step prepares all
+ * layers of a stage up front with one call. */
+int ifk_prepare_many_f32(const ifk_problem *p, int count, const float *weights, size_t weight_stride,
+                         float *prepared, size_t prepared_stride, ifk_stream_t stream);
+
 /* y = L^-1 x : the layer's training direction x -> z.
  * Replaces inv_conv_with_bp.inverse (inv_conv_with_bp_general.cpp:19-28 ->
- * inv_conv_cuda_inverse, inv_conv_with_bp_kernel_general.cu:72-129).  x and y may alias. */
+ * inv_conv_cuda_inverse, inv_conv_with_bp_kernel_general.cu:72-129).  x and y must not alias. */
 int ifk_inverse_f32(const ifk_problem *p, const float *x, const float *prepared, float *y,
                     ifk_stream_t stream);
 
@@ -90,7 +97,7 @@ int ifk_conv_f32(const ifk_problem *p, const float *y, const float *weight, floa
 
 /* dX = L^-T g : gradient w.r.t. the layer input.
  * Replaces inv_conv_with_bp.dy (inv_conv_with_bp_general.cpp:70-81 -> inv_conv_dy,
- * .cu:388-483), computing the true adjoint.  g and dx may alias. */
+ * .cu:388-483), computing the true adjoint.  g and dx must not alias. */
 int ifk_bwd_input_f32(const ifk_problem *p, const float *g, const float *prepared, float *dx,
                       ifk_stream_t stream);
 
@@ -103,6 +110,16 @@ size_t ifk_bwd_weight_workspace_bytes(const ifk_problem *p);
 int ifk_bwd_weight_f32(const ifk_problem *p, const float *dx, const float *y, float *dw,
                        void *workspace, ifk_stream_t stream);
 
+/* The two stages of ifk_bwd_weight_f32 separately, so a training step can run stage 1 of every
+ * layer on a side stream while the next layer's dX solve proceeds, and finish `count` layers of
+ * one geometry with ONE stage-2 launch: layer i reads workspaces + i*workspace_stride_bytes and
+ * writes dw + i*dw_stride (floats). */
+int ifk_bwd_weight_partial_f32(const ifk_problem *p, const float *dx, const float *y, void *workspace,
+                               ifk_stream_t stream);
+int ifk_bwd_weight_reduce_many_f32(const ifk_problem *p, int count, const void *workspaces,
+                                   size_t workspace_stride_bytes, float *dw, size_t dw_stride,
+                                   ifk_stream_t stream);
+
 /* dX and dW in one call (what inv_conv_.backward needs, inv_conv.py:62-81). */
 int ifk_backward_f32(const ifk_problem *p, const float *g, const float *y,
                      const float *prepared, float *dx, float *dw, void *workspace,
@@ -110,7 +127,7 @@ int ifk_backward_f32(const ifk_problem *p, const float *g, const float *y,
 
 /* ---- introspection (used by bench.py / tests; not needed by a binding) -----------------
  * Which kernel variant a solve of this geometry dispatches to, as a short static string,
- * e.g. "smem<cc=3,chunk=27> ns=4 slots=16 threads=256 smem=24KB" or "global". */
+ * e.g. "smem<cc=4,nv=6,vec=4> ns=4 nct=3 slots=16 iters=1 threads=192(192) ..." or "global ...". */
 int ifk_describe_solve(const ifk_problem *p, char *buf, size_t buflen);
 
 #ifdef __cplusplus

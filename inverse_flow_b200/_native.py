@@ -16,9 +16,10 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libifk_b200.so")
 
 EXPORTS = (
-    "ifk_version", "ifk_status_string", "ifk_prepared_floats", "ifk_prepare_f32",
+    "ifk_version", "ifk_status_string", "ifk_prepared_floats", "ifk_prepare_f32", "ifk_prepare_many_f32",
     "ifk_inverse_f32", "ifk_conv_f32", "ifk_bwd_input_f32", "ifk_bwd_weight_workspace_bytes",
-    "ifk_bwd_weight_f32", "ifk_backward_f32", "ifk_describe_solve",
+    "ifk_bwd_weight_f32", "ifk_bwd_weight_partial_f32", "ifk_bwd_weight_reduce_many_f32",
+    "ifk_backward_f32", "ifk_describe_solve",
 )
 
 
@@ -57,6 +58,12 @@ def load():
         fn = getattr(lib, name)
         fn.restype = ci
         fn.argtypes = [P] + [vp] * nptr + [vp]          # ..., stream
+    lib.ifk_prepare_many_f32.restype = ci
+    lib.ifk_prepare_many_f32.argtypes = [P, ci, vp, sz, vp, sz, vp]
+    lib.ifk_bwd_weight_partial_f32.restype = ci
+    lib.ifk_bwd_weight_partial_f32.argtypes = [P, vp, vp, vp, vp]
+    lib.ifk_bwd_weight_reduce_many_f32.restype = ci
+    lib.ifk_bwd_weight_reduce_many_f32.argtypes = [P, ci, vp, sz, vp, sz, vp]
     lib.ifk_describe_solve.restype = ci
     lib.ifk_describe_solve.argtypes = [P, ctypes.c_char_p, sz]
     _lib = lib

@@ -65,6 +65,18 @@ int ifk_prepare_f32(const ifk_problem *p, const float *weight, float *prepared, 
     return launch_prepare(g, weight, prepared, (cudaStream_t)stream);
 }
 
+int ifk_prepare_many_f32(const ifk_problem *p, int count, const float *weights, size_t weight_stride,
+                         float *prepared, size_t prepared_stride, ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (count < 0) return IFK_ERR_BAD_SHAPE;
+    if (count > 0 && (!weights || !prepared)) return IFK_ERR_NULL_POINTER;
+    if ((long long)count * g.groups > 0x7fffffffLL) return IFK_ERR_UNSUPPORTED;
+    return launch_prepare(g, weights, prepared, (cudaStream_t)stream, count, weight_stride, prepared_stride);
+}
+
 int ifk_inverse_f32(const ifk_problem *p, const float *x, const float *prepared, float *y,
                     ifk_stream_t stream)
 {
@@ -110,6 +122,29 @@ int ifk_bwd_weight_f32(const ifk_problem *p, const float *dx, const float *y, fl
     if (st != IFK_OK) return st;
     if (!dw || !workspace || (g.B > 0 && (!dx || !y))) return IFK_ERR_NULL_POINTER;
     return launch_bwd_weight(g, dx, y, dw, workspace, (cudaStream_t)stream);
+}
+
+int ifk_bwd_weight_partial_f32(const ifk_problem *p, const float *dx, const float *y, void *workspace,
+                               ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!workspace || (g.B > 0 && (!dx || !y))) return IFK_ERR_NULL_POINTER;
+    return launch_bwd_weight_partial(g, dx, y, workspace, (cudaStream_t)stream);
+}
+
+int ifk_bwd_weight_reduce_many_f32(const ifk_problem *p, int count, const void *workspaces,
+                                   size_t workspace_stride_bytes, float *dw, size_t dw_stride,
+                                   ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (count < 0 || count > 65535 || workspace_stride_bytes % sizeof(float) != 0) return IFK_ERR_BAD_SHAPE;
+    if (count > 0 && (!workspaces || !dw)) return IFK_ERR_NULL_POINTER;
+    return launch_bwd_weight_reduce(g, count, workspaces, workspace_stride_bytes, dw, dw_stride,
+                                    (cudaStream_t)stream);
 }
 
 int ifk_backward_f32(const ifk_problem *p, const float *grad, const float *y, const float *prepared,

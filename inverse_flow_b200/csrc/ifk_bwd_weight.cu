@@ -213,8 +213,10 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
 
 __global__ void __launch_bounds__(256)
 bwd_weight_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int nchunks,
-                         int C, int Cg, int Cw, int KH, int KW)
+                         int C, int Cg, int Cw, int KH, int KW, size_t partial_stride, size_t dw_stride)
 {
+    partial += (size_t)blockIdx.y * partial_stride;        // batched: blockIdx.y = layer
+    dw += (size_t)blockIdx.y * dw_stride;
     const int K = KH * KW;
     const int total = C * Cw * K;
     const size_t chunk_stride = (size_t)C * Cg * K;
@@ -243,43 +245,55 @@ bwd_weight_reduce_kernel(const float *__restrict__ partial, float *__restrict__ 
     }
 }
 
+int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y, void *workspace, cudaStream_t s)
+{
+    if (g.B == 0) return 0;
+    const BwdWeightPlan pl = make_plan(g);
+    BwdWeightParams p{};
+    p.dx = dx; p.y = y; p.partial = (float *)workspace;
+    p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW; p.Cg = g.Cg;
+    p.nt = pl.nt; p.items = pl.items; p.per_warp = pl.per_warp; p.per_chunk = pl.per_chunk;
+    p.nbuf = pl.nbuf; p.XN = pl.XN;
+    const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
+    p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) ? 1 : 0;
+    if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
+    dim3 grid(pl.nchunks, g.groups, pl.nz);
+    void (*kern)(const BwdWeightParams) = bwd_weight_partial_kernel<4>;
+    switch (pl.per_warp) {
+        case 1: kern = bwd_weight_partial_kernel<1>; break;
+        case 2: kern = bwd_weight_partial_kernel<2>; break;
+        case 3: kern = bwd_weight_partial_kernel<3>; break;
+        default: break;
+    }
+    if (pl.smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<grid, kWarps * 32, pl.smem_bytes, s>>>(p);
+    return cuda_status(cudaGetLastError());
+}
+
+int launch_bwd_weight_reduce(const Geometry &g, int count, const void *workspace, size_t workspace_stride,
+                             float *dw, size_t dw_stride, cudaStream_t s)
+{
+    if (count <= 0) return 0;
+    const BwdWeightPlan pl = make_plan(g);
+    const int total = g.C * g.Cw * g.K;
+    int blocks = (total + 255) / 256;
+    if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+    dim3 grid(blocks, count);
+    bwd_weight_reduce_kernel<<<grid, 256, 0, s>>>((const float *)workspace, dw, g.B > 0 ? pl.nchunks : 0, g.C,
+                                                  g.Cg, g.Cw, g.KH, g.KW, workspace_stride / sizeof(float),
+                                                  dw_stride);
+    return cuda_status(cudaGetLastError());
+}
+
 int launch_bwd_weight(const Geometry &g, const float *dx, const float *y, float *dw,
                       void *workspace, cudaStream_t s)
 {
-    const BwdWeightPlan pl = make_plan(g);
-    float *partial = (float *)workspace;
-    const int total = g.C * g.Cw * g.K;
-    if (g.B > 0) {
-        BwdWeightParams p{};
-        p.dx = dx; p.y = y; p.partial = partial;
-        p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW; p.Cg = g.Cg;
-        p.nt = pl.nt; p.items = pl.items; p.per_warp = pl.per_warp; p.per_chunk = pl.per_chunk;
-        p.nbuf = pl.nbuf; p.XN = pl.XN;
-        const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
-        p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) ? 1 : 0;
-        if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
-        dim3 grid(pl.nchunks, g.groups, pl.nz);
-        void (*kern)(const BwdWeightParams) = bwd_weight_partial_kernel<4>;
-        switch (pl.per_warp) {
-            case 1: kern = bwd_weight_partial_kernel<1>; break;
-            case 2: kern = bwd_weight_partial_kernel<2>; break;
-            case 3: kern = bwd_weight_partial_kernel<3>; break;
-            default: break;
-        }
-        if (pl.smem_bytes > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)pl.smem_bytes);
-            if (e != cudaSuccess) return (int)e;
-        }
-        kern<<<grid, kWarps * 32, pl.smem_bytes, s>>>(p);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-    }
-    int blocks = (total + 255) / 256;
-    if (blocks > kNumSM * 8) blocks = kNumSM * 8;
-    bwd_weight_reduce_kernel<<<blocks, 256, 0, s>>>(partial, dw, g.B > 0 ? pl.nchunks : 0, g.C, g.Cg,
-                                                    g.Cw, g.KH, g.KW);
-    return cuda_status(cudaGetLastError());
+    int st = launch_bwd_weight_partial(g, dx, y, workspace, s);
+    if (st != 0) return st;
+    return launch_bwd_weight_reduce(g, 1, workspace, 0, dw, 0, s);
 }
 
 }  // namespace ifk

@@ -26,13 +26,17 @@ inline const float *prepared_dir(const Geometry &g, const float *prepared, int d
 }
 
 // launchers (each returns 0 or a cudaError_t)
-int launch_prepare(const Geometry &g, const float *weight, float *prepared, cudaStream_t s);
+int launch_prepare(const Geometry &g, const float *weight, float *prepared, cudaStream_t s, int count = 1,
+                   size_t weight_stride = 0, size_t prepared_stride = 0);
 int launch_solve(const Geometry &g, const float *in, const float *prep_dir, float *out,
                  bool reverse, cudaStream_t s);
 int launch_conv(const Geometry &g, const float *y, const float *weight, float *x, cudaStream_t s);
 size_t bwd_weight_workspace_bytes(const Geometry &g);
 int launch_bwd_weight(const Geometry &g, const float *dx, const float *y, float *dw,
                       void *workspace, cudaStream_t s);
+int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y, void *workspace, cudaStream_t s);
+int launch_bwd_weight_reduce(const Geometry &g, int count, const void *workspace, size_t workspace_stride,
+                             float *dw, size_t dw_stride, cudaStream_t s);
 int describe_solve(const Geometry &g, char *buf, size_t buflen);
 void set_solve_probe(long long *device_buffer);
 

@@ -11,7 +11,8 @@
 // Prepared layout (floats): [dir][group][co][KDP], row = [tap t][ci]; tap 0 holds T (it
 // multiplies the right-hand side x), taps t >= 1 hold -(T W_q) for q = (t / KW, t % KW).
 //
-// Grid (groups, 2 directions, tap slabs).  Every CTA rebuilds T in shared memory (forward
+// Grid (groups x layers, 2 directions, tap slabs): several layers' weights of one geometry can
+// be prepared by a single launch.  Every CTA rebuilds T in shared memory (forward
 // substitution, one thread per column, 4 independent partial sums: ~Cg^2/2 cycles) and then
 // forms its slab of taps as small dense products out of shared memory.
 #include "ifk_internal.cuh"
@@ -22,14 +23,17 @@ constexpr int kPrepThreads = 256;
 
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_kernel(const float *__restrict__ weight, float *__restrict__ prepared, int C, int Cg, int Cw,
-               int KH, int KW, int KD, int KDP, int taps_per_cta)
+               int KH, int KW, int KD, int KDP, int taps_per_cta, int groups, size_t weight_stride,
+               size_t prepared_stride)
 {
     extern __shared__ float sm[];
     const int TS = Cg + 1;                 // padded row stride: column walks hit distinct banks
     float *A = sm;                         // [Cg][TS] strictly-lower centre tap A0
     float *T = A + Cg * TS;                // [Cg][TS] T0 = (I + A0)^-1 (unit lower triangular)
     float *Wq = T + Cg * TS;               // [Cg][TS] one tap, rows = weight output channel
-    const int G = blockIdx.x, dir = blockIdx.y;
+    const int G = blockIdx.x % groups, layer = blockIdx.x / groups, dir = blockIdx.y;
+    weight += (size_t)layer * weight_stride;       // batched: one weight tensor per layer
+    prepared += (size_t)layer * prepared_stride;
     const int K = KH * KW;
     const size_t tap_stride = (size_t)K;                   // between input columns
     const size_t row_stride = (size_t)Cw * tap_stride;     // between output rows
@@ -108,8 +112,10 @@ prepare_kernel(const float *__restrict__ weight, float *__restrict__ prepared, i
     }
 }
 
-int launch_prepare(const Geometry &g, const float *weight, float *prepared, cudaStream_t s)
+int launch_prepare(const Geometry &g, const float *weight, float *prepared, cudaStream_t s, int count,
+                   size_t weight_stride, size_t prepared_stride)
 {
+    if (count <= 0) return 0;
     const size_t smem = (size_t)3 * g.Cg * (g.Cg + 1) * sizeof(float);
     if (smem > (size_t)kMaxSmemBytes) return IFK_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) {
@@ -118,11 +124,14 @@ int launch_prepare(const Geometry &g, const float *weight, float *prepared, cuda
         if (e != cudaSuccess) return (int)e;
     }
     // small problems: one CTA per (group, direction) walks all taps; otherwise one tap per CTA
-    const long work = (long)g.Cg * g.Cg * g.Cg * g.K;
-    const int taps_per_cta = work <= 64 * 1024 ? g.K : 1;
-    dim3 grid(g.groups, 2, (g.K + taps_per_cta - 1) / taps_per_cta);
+    // one tap per CTA unless that would mean far more CTAs than the GPU holds at once
+    int taps_per_cta = 1;
+    while ((long)g.groups * count * 2 * ((g.K + taps_per_cta - 1) / taps_per_cta) > 8L * kNumSM && taps_per_cta < g.K)
+        taps_per_cta++;
+    dim3 grid(g.groups * count, 2, (g.K + taps_per_cta - 1) / taps_per_cta);
     prepare_kernel<<<grid, kPrepThreads, smem, s>>>(weight, prepared, g.C, g.Cg, g.Cw, g.KH, g.KW, g.KD,
-                                                    g.KDP, taps_per_cta);
+                                                    g.KDP, taps_per_cta, g.groups, weight_stride,
+                                                    prepared_stride);
     return cuda_status(cudaGetLastError());
 }
 

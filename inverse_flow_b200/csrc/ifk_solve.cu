@@ -72,7 +72,7 @@ solve_global_kernel(const SolveParams p)
 // ------------------------------------------------------------------------------------------
 struct SolveConfig {
     bool smem;      // false -> global fallback
-    int cc, nv, vec, ns, nct, nslots, iters, threads;
+    int cc, nv, vec, ns, nct, nslots, iters, threads, nwork;
     int WP, PS, YN, XN, CgV, NVT, CgP4;
     size_t smem_bytes;
     int grid_x;
@@ -172,6 +172,14 @@ static SolveConfig choose_config(const Geometry &g)
         }
     }
     if (!best.smem) return best;
+    // helper warps: staging, the pre-pass and the zero fill are latency bound with few threads
+    best.nwork = best.threads;
+    {
+        const int tmax = solve_variant_max_threads(best.cc, best.nv, best.vec);
+        int want = 128;
+        if (want > tmax) want = tmax;
+        if (best.threads < want) best.threads = want;
+    }
     // CTAs resident per SM (shared memory and thread limits), then one stripe of images each
     int per_sm = (int)((size_t)(kMaxSmemBytes + 1024) / (best.smem_bytes + 1024));
     const int by_threads = 2048 / best.threads;
@@ -183,6 +191,14 @@ static SolveConfig choose_config(const Geometry &g)
     if (grid_x < 1) grid_x = 1;
     best.grid_x = grid_x;
     return best;
+}
+
+bool solve_use_pdl()
+{
+    // programmatic dependent launch: measured slightly SLOWER on the chained model shapes
+    // (0.658 vs 0.610 ms per glow_mnist step), so it is opt-in
+    const char *e = getenv("IFK_PDL");
+    return e && e[0] == '1';
 }
 
 static long long *g_probe = nullptr;   // tuning aid, see ifk_debug_set_probe
@@ -205,7 +221,7 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
         return cuda_status(cudaGetLastError());
     }
     p.WP = c.WP; p.PS = c.PS; p.YN = c.YN; p.XN = c.XN; p.CgV = c.CgV; p.NVT = c.NVT; p.CgP4 = c.CgP4;
-    p.NS = c.ns; p.NCT = c.nct; p.nslots = c.nslots; p.iters = c.iters;
+    p.NS = c.ns; p.NCT = c.nct; p.nslots = c.nslots; p.iters = c.iters; p.nwork = c.nwork;
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0) ? 1 : 0;
     if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
@@ -221,8 +237,8 @@ int describe_solve(const Geometry &g, char *buf, size_t buflen)
 {
     const SolveConfig c = choose_config(g);
     if (c.smem)
-        snprintf(buf, buflen, "smem<cc=%d,nv=%d,vec=%d> ns=%d nct=%d slots=%d iters=%d threads=%d smem=%zuB grid=%dx%d",
-                 c.cc, c.nv, c.vec, c.ns, c.nct, c.nslots, c.iters, c.threads, c.smem_bytes, c.grid_x, g.groups);
+        snprintf(buf, buflen, "smem<cc=%d,nv=%d,vec=%d> ns=%d nct=%d slots=%d iters=%d threads=%d(%d) smem=%zuB grid=%dx%d",
+                 c.cc, c.nv, c.vec, c.ns, c.nct, c.nslots, c.iters, c.threads, c.nwork, c.smem_bytes, c.grid_x, g.groups);
     else
         snprintf(buf, buflen, "global threads=%d grid=%dx%d", c.threads, c.grid_x, g.groups);
     return 0;

@@ -38,6 +38,7 @@ struct SolveParams {
     int NVT;            // (K - 1) * CgV : vector entries of one output row's reduction
     int CgP4;           // Cg rounded up to 4 (row stride of the transposed T in smem)
     int NS, NCT, nslots, iters;
+    int nwork;          // threads that walk the wavefront (multiple of 32); the rest only help staging
     int reverse;
     int bulk;           // image size / pointers allow TMA bulk copies (16-byte granularity)
     long long *probe;   // tuning aid: clock64() stamps of CTA (0,0) thread 0, or nullptr
@@ -91,6 +92,16 @@ __device__ __forceinline__ void fence_async_proxy()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+// Pin loop-invariant values in registers.  Left alone, ptxas re-reads kernel parameters from the
+// constant bank inside the diagonal loop (rematerialisation), and those loads -- tens of cycles
+// each -- sit on the loop-carried critical path of a latency-bound kernel.  Adding a zero that
+// was read back from shared memory through a volatile load makes the value opaque.
+struct Hold {
+    int zero;
+    __device__ __forceinline__ int operator()(int v) const { return v + zero; }
+    __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return v + (uint32_t)zero; }
+};
 
 // ---- vector loads from shared memory by 32-bit shared-space address -------------------------
 template <int VEC>
@@ -214,14 +225,11 @@ solve_smem_kernel(const SolveParams p)
     const float *in0 = p.in + (size_t)G * Cg * HW;
     float *out0 = p.out + (size_t)G * Cg * HW;
 
-    int b = blockIdx.x;
-    if (p.bulk && tid == 0) {
-        mbar_init(bar, 1);
-        if (b < p.B) {
-            mbar_expect_tx(bar, img_bytes);
-            bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
-        }
-    }
+    // Programmatic dependent launch: let the next kernel of the stream start launching now, and do
+    // everything that touches no global memory (index tables, zero fill) before waiting for the
+    // previous kernel's results.  Both instructions are no-ops in a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) smem[2] = 0.f;          // source of the opaque zero used by Hold (see above)
 
     // tables: where a vector entry lives relative to the pixel, and which weights it meets
     for (int v = tid; v < p.NVT; v += nthr) {
@@ -229,6 +237,21 @@ solve_smem_kernel(const SolveParams p)
         const int qh = t / p.KW, qw = t - qh * p.KW;
         tbl_off[v] = ((-qh * WP - qw) * PS + q * VEC) * 4;
         tbl_w[v] = (t - 1) * Cg + q * VEC;
+    }
+    // ybuf starts from zero for every image: the halo, and the not-yet-written interior that
+    // zero-weight padding entries may touch
+    for (int i = tid * 4; i < p.YN; i += nthr * 4)
+        *reinterpret_cast<float4 *>(ybuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    int b = blockIdx.x;
+    if (p.bulk && tid == 0) {
+        mbar_init(bar, 1);
+        if (b < p.B) {
+            mbar_expect_tx(bar, img_bytes);
+            bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
+        }
     }
     if (Cg > 1)
         for (int i = tid; i < Cg * p.CgP4; i += nthr) {
@@ -274,27 +297,29 @@ solve_smem_kernel(const SolveParams p)
     const int own_c0 = ct * CC + own_off;
 
     IFK_PROBE(2);
-    const int ndiag = H + W - 1;
-    const int iters = p.iters, nslots = p.nslots;
-    const uint32_t ybase = smem_u32(ybuf) + (uint32_t)(((p.KH - 1) * WP + (p.KW - 1)) * PS) * 4u;
-    const uint32_t zstride = (uint32_t)HW * 4u;
+    Hold hold;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hold.zero) : "r"(smem_u32(smem + 2)) : "memory");
+    const int ndiag = hold(H + W - 1);
+    const int iters = hold(p.iters), nslots = hold(p.nslots), nwork = hold(p.nwork), Wr = hold(W);
+    const int NSr = hold(NS >> 1);
+    own_size = hold(own_size);
+    const uint32_t ybase = hold(smem_u32(ybuf) + (uint32_t)(((p.KH - 1) * WP + (p.KW - 1)) * PS) * 4u);
+    const uint32_t zstride = hold((uint32_t)HW * 4u);
     // rows of this thread: slot, slot + nslots, ...; row_ok = how many of them exist
-    const int row_ok = worker && slot < H ? (H - 1 - slot) / nslots + 1 : 0;
+    const int row_ok = hold(worker && slot < H ? (H - 1 - slot) / nslots + 1 : 0);
     // pixel (h, w = d - h): ybuf address = ybase + ((h*WP + w)*PS)*4 ; contiguous index rr = h*W + w
-    const uint32_t pix_step = (uint32_t)PS * 4u;                                   // per diagonal
-    const uint32_t pix_row = (uint32_t)(nslots * (WP - 1) * PS) * 4u;              // per row iteration
-    const uint32_t pix0 = ybase + (uint32_t)(slot * (WP - 1) * PS) * 4u;           // d = 0, it = 0
-    const uint32_t z_step = p.reverse ? (uint32_t)(-4) : 4u;
-    const uint32_t z_row = (uint32_t)(nslots * (W - 1)) * z_step;
+    const uint32_t pix_step = hold((uint32_t)PS * 4u);                                   // per diagonal
+    const uint32_t pix_row = hold((uint32_t)(nslots * (WP - 1) * PS) * 4u);              // per row iteration
+    const uint32_t pix0 = ybase + (uint32_t)(slot * (WP - 1) * PS) * 4u;                 // d = 0, it = 0
+    const uint32_t z_step = hold(p.reverse ? (uint32_t)(-4) : 4u);
+    const uint32_t z_row = hold((uint32_t)(nslots * (W - 1)) * z_step);
     const uint32_t z0 = smem_u32(zbuf) + (uint32_t)(own_c0 * HW) * 4u +
                         (p.reverse ? (uint32_t)(HW - 1 - slot * (W - 1)) * 4u : (uint32_t)(slot * (W - 1)) * 4u);
+    const uint32_t own_c0_bytes = hold((uint32_t)own_c0 * 4u);
+    const int slot_r = hold(slot);
     uint32_t parity = 0;
     for (; b < p.B; b += gridDim.x) {
         const int b_next = b + gridDim.x;
-        // ybuf starts from zero for every image: the halo, and the not-yet-written interior that
-        // zero-weight padding entries may touch
-        for (int i = tid * 4; i < p.YN; i += nthr * 4)
-            *reinterpret_cast<float4 *>(ybuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         IFK_PROBE(3);
         if (p.bulk) {
             mbar_wait(bar, parity);
@@ -313,6 +338,7 @@ solve_smem_kernel(const SolveParams p)
                 const int c4 = i / HW, r = i - c4 * HW;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                 const float *tp = tT + c4 * 4;
+#pragma unroll 4
                 for (int ci = 0; ci < Cg; ci++) {
                     const float xv = xbuf[ci * HW + r];
                     const float4 t4 = *reinterpret_cast<const float4 *>(tp + ci * p.CgP4);
@@ -339,12 +365,13 @@ solve_smem_kernel(const SolveParams p)
         // shuffles and stores with a handful of integer instructions.
         IFK_PROBE(5);
         uint32_t pix_d = pix0, z_d = z0;
+        if (tid < nwork)                         // helper warps skip the wavefront altogether
         for (int d = 0; d < ndiag; d++) {
             uint32_t pix = pix_d, za = z_d;
-            int col = d - slot;                 // column of this thread's row `it` on diagonal d
+            int col = d - slot_r;               // column of this thread's row `it` on diagonal d
 #pragma unroll 1
             for (int it = 0; it < iters; it++, pix += pix_row, za += z_row, col -= nslots) {
-                const bool active = row_ok > it && (unsigned)col < (unsigned)W;
+                const bool active = row_ok > it && (unsigned)col < (unsigned)Wr;
                 if (!__any_sync(0xffffffffu, active)) continue;        // warp-uniform
                 const uint32_t pa = active ? pix : ybase;              // idle lanes: a legal pixel
 
@@ -372,14 +399,20 @@ solve_smem_kernel(const SolveParams p)
 #pragma unroll
                     for (int a = 1; a < NACC; a++) acc[cc] += part[a][cc];
                 }
-                Rs<CC, 5>::run(acc, zv, ks, NS >> 1, own_size, active, pa + own_c0 * 4u, za, zstride);
+                Rs<CC, 5>::run(acc, zv, ks, NSr, own_size, active, pa + own_c0_bytes, za, zstride);
             }
             pix_d += pix_step;
             z_d += z_step;
-            if (nthr <= 32) __syncwarp(); else __syncthreads();
+            if (nwork <= 32) __syncwarp();
+            else asm volatile("bar.sync 1, %0;" ::"r"(nwork) : "memory");     // worker warps only
         }
 
         IFK_PROBE(6);
+        if (b_next < p.B) {                  // the stripe goes on: ybuf back to zero for the next image
+            __syncthreads();
+            for (int i = tid * 4; i < p.YN; i += nthr * 4)
+                *reinterpret_cast<float4 *>(ybuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float *dst = out0 + (size_t)b * img_stride;
         if (p.bulk) {
             fence_async_proxy();            // generic-proxy writes of zbuf -> visible to the TMA engine
@@ -410,7 +443,7 @@ solve_smem_kernel(const SolveParams p)
 int launch_solve_vec1(int cc, int nv, const SolveParams &p, dim3 grid, int threads, size_t smem, cudaStream_t s);
 int launch_solve_vec2(int cc, int nv, const SolveParams &p, dim3 grid, int threads, size_t smem, cudaStream_t s);
 int launch_solve_vec4(int cc, int nv, const SolveParams &p, dim3 grid, int threads, size_t smem, cudaStream_t s);
-bool solve_variant_exists(int cc, int nv, int vec);
+bool solve_use_pdl();
 int solve_variant_max_threads(int cc, int nv, int vec);
 
 template <int CC, int NV, int VEC>
@@ -421,8 +454,17 @@ int launch_solve_variant(const SolveParams &p, dim3 grid, int threads, size_t sm
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<grid, threads, smem, s>>>(p);
-    return cuda_status(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL, see the kernel prologue
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = solve_use_pdl() ? 1 : 0;
+    return cuda_status(cudaLaunchKernelEx(&cfg, kern, p));
 }
 
 }  // namespace ifk

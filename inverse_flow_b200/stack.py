@@ -7,10 +7,14 @@ with every buffer preallocated, all launches going straight through the C ABI, a
 forward + backward captured in one CUDA graph (B200-first: streams and graphs instead of a
 per-layer Python loop).  It is what bench.py times and what a training driver would replay.
 
-Forward per layer  : prepare(W) ; y = L^-1 x                (x of layer i+1 = y of layer i)
-Backward per layer : dX = L^-T g ; dW = -corr(dX, y)        (g of layer i-1 = dX of layer i)
-dW of every layer is written into one flat bucket (`grad_bucket`), i.e. directly into the
-buffer a data-parallel all-reduce consumes.
+Per step            : one batched prepare per stage (weights do not depend on activations)
+Forward per layer   : y = L^-1 x                            (x of layer i+1 = y of layer i)
+Backward per layer  : dX = L^-T g on the main stream        (g of layer i-1 = dX of layer i);
+                      stage 1 of dW = -corr(dX, y) on a SIDE stream, overlapping the next
+                      layer's solve (a fork/join in the captured graph);
+End of backward     : one batched stage-2 reduction per stage writes dW of every layer into
+                      one flat bucket (`grad_bucket`), i.e. directly into the buffer a
+                      data-parallel all-reduce consumes.
 """
 import ctypes
 
@@ -53,22 +57,27 @@ class InvConvStack:
             ws = self.lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(st.problem))
             if pf == 0:
                 raise ValueError("unsupported stage %s" % ((C, H, W, k, n),))
-            st.w, st.dw, st.prepared = [], [], []
-            for _ in range(n):
-                sz = C * C * k * k
-                st.w.append(self.weights[off:off + sz].view(C, C, k, k))
-                st.dw.append(self.grad_bucket[off:off + sz].view(C, C, k, k))
-                st.w[-1].copy_(reference_init_weight(C, k, gen))
-                st.prepared.append(torch.empty(pf, dtype=torch.float32, device=self.device))
-                off += sz
+            sz = C * C * k * k
+            st.w_base, st.dw_base, st.w_stride = self.weights[off:], self.grad_bucket[off:], sz
+            st.w = [self.weights[off + i * sz: off + (i + 1) * sz].view(C, C, k, k) for i in range(n)]
+            st.dw = [self.grad_bucket[off + i * sz: off + (i + 1) * sz].view(C, C, k, k) for i in range(n)]
+            for wt in st.w:
+                wt.copy_(reference_init_weight(C, k, gen))
+            off += n * sz
+            st.prepared_all = torch.empty(n * pf, dtype=torch.float32, device=self.device)
+            st.prepared = [st.prepared_all[i * pf:(i + 1) * pf] for i in range(n)]
+            st.pf = pf
             shape = (self.batch, C, H, W)
             st.act = [torch.zeros(shape, device=self.device) for _ in range(n + 1)]   # act[0] = x
-            st.grad = [torch.zeros(shape, device=self.device) for _ in range(2)]     # ping-pong
+            st.dxs = [torch.zeros(shape, device=self.device) for _ in range(n)]       # dX of every layer
             st.grad_in = torch.zeros(shape, device=self.device)                       # upstream g
-            st.workspace = torch.empty((ws + 3) // 4, dtype=torch.float32, device=self.device)
+            st.ws_floats = (ws + 15) // 16 * 4                                        # 16-byte multiple
+            st.workspace = torch.empty(n * st.ws_floats, dtype=torch.float32, device=self.device)
             self.stages.append(st)
+        self.side = torch.cuda.Stream(device=self.device)
         self.graph = None
-        self.launches_per_step = sum(st.n * 5 for st in self.stages)
+        # per stage: 1 prepare + n inverse + n dX + n dW stage 1 + 1 dW stage 2
+        self.launches_per_step = sum(3 * st.n + 2 for st in self.stages)
 
     # -- raw launches ------------------------------------------------------------------
     def _stream(self):
@@ -78,23 +87,34 @@ class InvConvStack:
         lib, s = self.lib, self._stream()
         for st in self.stages:
             p = ctypes.byref(st.problem)
+            _native.check(lib.ifk_prepare_many_f32(p, st.n, st.w_base.data_ptr(), st.w_stride,
+                                                   st.prepared_all.data_ptr(), st.pf, s))
             for i in range(st.n):
-                _native.check(lib.ifk_prepare_f32(p, st.w[i].data_ptr(), st.prepared[i].data_ptr(), s))
                 _native.check(lib.ifk_inverse_f32(p, st.act[i].data_ptr(), st.prepared[i].data_ptr(),
                                                   st.act[i + 1].data_ptr(), s))
 
     def backward(self):
-        lib, s = self.lib, self._stream()
+        lib = self.lib
+        main = torch.cuda.current_stream(self.device)
+        s = ctypes.c_void_p(main.cuda_stream)
+        side_s = ctypes.c_void_p(self.side.cuda_stream)
         for st in self.stages:
             p = ctypes.byref(st.problem)
             g = st.grad_in
             for i in reversed(range(st.n)):
-                dx = st.grad[i & 1]
-                _native.check(lib.ifk_backward_f32(p, g.data_ptr(), st.act[i + 1].data_ptr(),
-                                                   st.prepared[i].data_ptr(), dx.data_ptr(),
-                                                   st.dw[i].data_ptr(), st.workspace.data_ptr(), s))
+                dx = st.dxs[i]
+                _native.check(lib.ifk_bwd_input_f32(p, g.data_ptr(), st.prepared[i].data_ptr(), dx.data_ptr(), s))
+                self.side.wait_stream(main)                       # fork: dW stage 1 needs this dX
+                ws = st.workspace[i * st.ws_floats:]
+                _native.check(lib.ifk_bwd_weight_partial_f32(p, dx.data_ptr(), st.act[i + 1].data_ptr(),
+                                                             ws.data_ptr(), side_s))
                 g = dx
             st.dx = g
+        main.wait_stream(self.side)                               # join
+        for st in self.stages:
+            _native.check(lib.ifk_bwd_weight_reduce_many_f32(
+                ctypes.byref(st.problem), st.n, st.workspace.data_ptr(), st.ws_floats * 4,
+                st.dw_base.data_ptr(), st.w_stride, s))
 
     def forward_backward(self):
         self.forward()

@@ -16,8 +16,8 @@
  *                          centre-tap triangular mask of solve_mc.py:104-108.
  *   dX, dW               : the reference has NO CPU backward.  They are the adjoint
  *                          of the solver above and
- *                          are pinned by autograd through solve_mc.py's own solver,
- *                          see tests/golden/make_golden.py.
+ *                          are pinned by the derivative of solve_mc.py's own solver
+ *                          (linearity + finite differences), tests/golden/make_golden.py.
  *   literal_* functions  : bug-for-bug restatement of the shipped CUDA kernels
  *                          inv_conv_with_bp_kernel_general.cu:52-65 (inverse),
  *                          :307-327 + :371-383 (dy) -- compat mode only.
