@@ -48,6 +48,12 @@ WORKLOADS = {
                   "if_cnn_mnist inverse-conv layers, batch 64/GPU"),
 }
 
+# DRAM bytes (read + write) of ONE launch of the dominant kernel, from a committed ncu --set full
+# capture of that kernel at the workload's stage-1 shape: workload -> (bytes, where it is recorded)
+PROFILED_DRAM_TRAFFIC = {
+    "glow_mnist": (349184, "profiles/r01_solve_final_100x4x14x14_k2.txt (dram__bytes_read 349184 + write 0)"),
+}
+
 CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
                "clocks_event_reasons.sw_power_cap")
@@ -360,7 +366,9 @@ def run_ours(args):
     n_solves = sum(2 * s.n for s in stack.stages)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": PROFILED_DRAM_TRAFFIC.get(args.workload, (None, None))[0] if args.groups == 1 else None,
+        "traffic_source": PROFILED_DRAM_TRAFFIC.get(args.workload, (None, None))[1] if args.groups == 1 else None,
+        "peak_source": peak_src,
         "kernel": "solve_smem_kernel (wavefront triangular solve; inverse and bwd_input)",
         "variant": _native.describe_solve(st0.problem),
         "kernel_us": solve_ms * 1e3, "algorithmic_bytes_per_launch": solve_bytes,
