@@ -5,30 +5,29 @@
 // batch-summed correlation of the input gradient with the saved output.
 //
 // Stage 1  bwd_weight_partial_kernel: CTA = (batch chunk, group, slab of work items).  A work
-//          item is one tap q with a 4x4 tile of (c, kc); a warp owns up to NI consecutive items
-//          and keeps their 16*NI accumulators in registers across the whole chunk; its lanes
-//          stride over the pixels, so every shared-memory read is a conflict-free row of 32
-//          distinct words.  The chunk's images (dX and y, both contiguous NCHW group slices)
+//          item is one tap q with a TC x TK tile of (c, kc) (4 x 12 for Cg >= 12); a warp owns
+//          one item and keeps its TC*TK accumulators in registers across the whole chunk; its
+//          lanes stride over the pixels, so every shared-memory read is a conflict-free row of
+//          32 distinct words and one pixel costs TC+TK loads for TC*TK FMAs.  The chunk's images (dX and y, both contiguous NCHW group slices)
 //          arrive by TMA bulk copies, double buffered: image n+1 lands while image n is
-//          consumed.  One shuffle reduction per accumulator at the very end.
+//          consumed.  One recursive-halving shuffle reduction at the very end.
 // Stage 2  bwd_weight_reduce_kernel: sums the per-chunk partials in chunk order (fixed order,
 //          no atomics -> bit-reproducible), negates, masks, scatters into the weight layout.
 #include "ifk_solve_kernel.cuh"   // TMA / mbarrier primitives
 
 namespace ifk {
 
-constexpr int kTile = 4;         // (c, kc) register tile edge
-constexpr int kWarps = 16;       // warps per CTA
-constexpr int kNI = 4;           // max items per warp (16 accumulators each)
+constexpr int kWarps = 16;       // warps per CTA; one work item (tap x TC x TK tile) per warp
 
 struct BwdWeightPlan {
-    int nt;            // tiles per channel axis
-    int items;         // K * nt * nt
-    int per_warp;      // items per warp (<= kNI)
+    int tc, tk;        // register tile: TC dX channels x TK y channels
+    int ntc, ntk;      // tiles per channel axis
+    int items;         // K * ntc * ntk
     int nz;            // item slabs (grid.z)
     int nchunks;       // batch chunks (== partial buffers)
     int per_chunk;     // images per chunk
     int nbuf;          // 2: double buffered, 1: single, 0: images read from global memory
+    int CgP;           // channels padded to the tile sizes (padding rows stay zero in smem)
     int XN;            // floats per staged image (16-byte multiple)
     size_t smem_bytes;
 };
@@ -36,18 +35,20 @@ struct BwdWeightPlan {
 static BwdWeightPlan make_plan(const Geometry &g)
 {
     BwdWeightPlan pl{};
-    pl.nt = (g.Cg + kTile - 1) / kTile;
-    pl.items = g.K * pl.nt * pl.nt;
-    pl.per_warp = (pl.items + kWarps - 1) / kWarps;
-    if (pl.per_warp > kNI) pl.per_warp = kNI;
-    const int per_cta = kWarps * pl.per_warp;
-    pl.nz = (pl.items + per_cta - 1) / per_cta;
+    pl.tc = g.Cg >= 4 ? 4 : (g.Cg >= 2 ? 2 : 1);
+    pl.tk = g.Cg >= 12 ? 12 : (g.Cg >= 8 ? 8 : (g.Cg >= 4 ? 4 : pl.tc));
+    pl.ntc = (g.Cg + pl.tc - 1) / pl.tc;
+    pl.ntk = (g.Cg + pl.tk - 1) / pl.tk;
+    pl.items = g.K * pl.ntc * pl.ntk;
+    pl.nz = (pl.items + kWarps - 1) / kWarps;
     int want = (kNumSM + g.groups * pl.nz - 1) / (g.groups * pl.nz);
     if (want < 1) want = 1;
     if (want > g.B) want = g.B > 0 ? g.B : 1;
     pl.per_chunk = g.B > 0 ? (g.B + want - 1) / want : 1;
     pl.nchunks = g.B > 0 ? (g.B + pl.per_chunk - 1) / pl.per_chunk : 1;
-    pl.XN = round_up(round_up(g.Cg, kTile) * g.H * g.W, 4);   // channels padded to the tile: no clamps
+    const int cp1 = pl.ntc * pl.tc, cp2 = pl.ntk * pl.tk;
+    pl.CgP = cp1 > cp2 ? cp1 : cp2;
+    pl.XN = round_up(pl.CgP * g.H * g.W, 4);
     const size_t one = (size_t)2 * pl.XN * sizeof(float);          // dX + y of one image
     pl.nbuf = 2 * one + 64 <= (size_t)kMaxSmemBytes ? 2 : (one + 64 <= (size_t)kMaxSmemBytes ? 1 : 0);
     if (pl.per_chunk == 1 && pl.nbuf == 2) pl.nbuf = 1;
@@ -64,42 +65,54 @@ size_t bwd_weight_workspace_bytes(const Geometry &g)
 struct BwdWeightParams {
     const float *dx, *y;
     float *partial;
-    int B, C, H, W, KH, KW, Cg, nt, items, per_warp, per_chunk, nbuf, XN, bulk;
+    int B, C, H, W, KH, KW, Cg, ntk, items, per_chunk, nbuf, XN, bulk;
 };
 
-template <int NI>
+// sum N per-lane values over the 32 lanes by recursive halving: N/2 + N/4 + ... shuffles
+// (against 5N for butterflies); lane l ends with the totals of entries [off, off+size),
+// (off, size) = rs_owner(N, 32, l), in a[0 .. size)
+template <int N, int M>
+struct Halve {
+    __device__ __forceinline__ static void run(float *a, int lane)
+    {
+        constexpr int HALF = (N + 1) / 2;
+        const bool hi = (lane & (M / 2)) != 0;
+#pragma unroll
+        for (int i = 0; i < HALF; i++) {
+            const float lo_v = a[i];
+            const float hi_v = (i + HALF < N) ? a[i + HALF] : 0.f;
+            a[i] = (hi ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, hi ? lo_v : hi_v, M / 2);
+        }
+        Halve<HALF, M / 2>::run(a, lane);
+    }
+};
+template <int N>
+struct Halve<N, 1> {
+    __device__ __forceinline__ static void run(float *, int) {}
+};
+__host__ __device__ constexpr int halve_final(int n, int m) { return m > 1 ? halve_final((n + 1) / 2, m / 2) : n; }
+
+template <int TC, int TK>
 __global__ void __launch_bounds__(kWarps * 32)
 bwd_weight_partial_kernel(const BwdWeightParams p)
 {
     extern __shared__ __align__(128) float smem[];
-    const int H = p.H, W = p.W, HW = p.H * p.W, K = p.KH * p.KW, Cg = p.Cg, nt = p.nt;
+    const int W = p.W, HW = p.H * p.W, K = p.KH * p.KW, Cg = p.Cg;
     const int chunk = blockIdx.x, G = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);          // [2] one per buffer
     float *buf0 = smem + 16;                                      // buffer b: dX at b*2*XN, y behind it
 
-    // this warp's items: consecutive, so they mostly share the c tile
-    const int item0 = (blockIdx.z * kWarps + warp) * p.per_warp;
-    int aoff[NI], voff[NI], qhw[NI];
-    bool live[NI];
+    // this warp's work item: one tap, TC dX channels x TK y channels
+    const int item = blockIdx.z * kWarps + warp;
+    const bool live = item < p.items;
+    const int t = live ? item % K : 0, tile = live ? item / K : 0;
+    const int c0 = (tile / p.ntk) * TC, k0 = (tile % p.ntk) * TK;
+    const int qh = t / p.KW, qw = t - qh * p.KW;
+    const int aoff = c0 * HW, voff = k0 * HW - (qh * W + qw);
+    float acc[TC * TK];
 #pragma unroll
-    for (int j = 0; j < NI; j++) {
-        const int it = item0 + j;
-        live[j] = j < p.per_warp && it < p.items;
-        const int itc = live[j] ? it : 0;
-        const int t = itc % K, tile = itc / K;
-        const int qh = t / p.KW, qw = t - qh * p.KW;
-        aoff[j] = (tile / nt) * kTile * HW;                       // first dX channel of the tile
-        voff[j] = (tile % nt) * kTile * HW - (qh * W + qw);       // first y channel, shifted by the tap
-        qhw[j] = (qh << 16) | qw;
-    }
-    float acc[NI][kTile][kTile];
-#pragma unroll
-    for (int j = 0; j < NI; j++)
-#pragma unroll
-        for (int a = 0; a < kTile; a++)
-#pragma unroll
-            for (int b = 0; b < kTile; b++) acc[j][a][b] = 0.f;
+    for (int i = 0; i < TC * TK; i++) acc[i] = 0.f;
 
     const int b_begin = chunk * p.per_chunk;
     const int b_end = b_begin + p.per_chunk < p.B ? b_begin + p.per_chunk : p.B;
@@ -152,32 +165,32 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
             ys = y0 + (size_t)b * img_stride;
         }
 
-        for (int r = lane; r < HW; r += 32) {
-            const int h = r / W, w = r - h * W;
+        if (live) {
+            // lanes stride over the pixels: every shared-memory read is 32 consecutive words
+            int h = lane / W, w = lane - h * W;
+            for (int r = lane; r < HW; r += 32) {
+                if (h >= qh && w >= qw) {
+                    float a[TC], v[TK];
+                    if (staged) {
 #pragma unroll
-            for (int j = 0; j < NI; j++) {
-                if (!live[j] || h < (qhw[j] >> 16) || w < (qhw[j] & 0xffff)) continue;
-                float a[kTile], v[kTile];
-                if (staged) {
+                        for (int i = 0; i < TC; i++) a[i] = dxs[aoff + i * HW + r];
 #pragma unroll
-                    for (int i = 0; i < kTile; i++) {
-                        a[i] = dxs[aoff[j] + i * HW + r];
-                        v[i] = ys[voff[j] + i * HW + r];
+                        for (int k = 0; k < TK; k++) v[k] = ys[voff + k * HW + r];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < TC; i++)
+                            a[i] = c0 + i < Cg ? __ldg(dxs + aoff + i * HW + r) : 0.f;
+#pragma unroll
+                        for (int k = 0; k < TK; k++)
+                            v[k] = k0 + k < Cg ? __ldg(ys + voff + k * HW + r) : 0.f;
                     }
-                } else {
-                    const int cbase = aoff[j] / HW, kbase = (voff[j] + (qhw[j] >> 16) * W + (qhw[j] & 0xffff)) / HW;
 #pragma unroll
-                    for (int i = 0; i < kTile; i++) {
-                        const int ci = cbase + i < Cg ? i : Cg - 1 - cbase;   // clamped; dropped at the end
-                        const int ki = kbase + i < Cg ? i : Cg - 1 - kbase;
-                        a[i] = __ldg(dxs + aoff[j] + ci * HW + r);
-                        v[i] = __ldg(ys + voff[j] + ki * HW + r);
-                    }
+                    for (int i = 0; i < TC; i++)
+#pragma unroll
+                        for (int k = 0; k < TK; k++) acc[i * TK + k] = fmaf(a[i], v[k], acc[i * TK + k]);
                 }
-#pragma unroll
-                for (int i = 0; i < kTile; i++)
-#pragma unroll
-                    for (int k = 0; k < kTile; k++) acc[j][i][k] = fmaf(a[i], v[k], acc[j][i][k]);
+                w += 32;
+                while (w >= W) { w -= W; h++; }
             }
         }
         if (bulk && p.nbuf == 2) __syncthreads();      // everyone is done with `cur` before it is refilled
@@ -191,23 +204,19 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
         }
     }
 
+    if (!live) return;                                 // warp-uniform
+    Halve<TC * TK, 32>::run(acc, lane);
+    int off, size;
+    rs_owner(TC * TK, 32, lane, &off, &size);
     float *out = p.partial + ((size_t)chunk * p.C + (size_t)G * Cg) * Cg * K;   // [c][kc][t]
 #pragma unroll
-    for (int j = 0; j < NI; j++) {
-        if (!live[j]) continue;                       // warp-uniform
-        const int it = item0 + j;
-        const int t = it % K, tile = it / K;
-        const int c0 = (tile / nt) * kTile, k0 = (tile % nt) * kTile;
+    constexpr int kFinal = halve_final(TC * TK, 32);
 #pragma unroll
-        for (int i = 0; i < kTile; i++)
-#pragma unroll
-            for (int k = 0; k < kTile; k++) {
-                float s = acc[j][i][k];
-#pragma unroll
-                for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-                if (lane == 0 && c0 + i < Cg && k0 + k < Cg)
-                    out[((size_t)(c0 + i) * Cg + (k0 + k)) * K + t] = s;
-            }
+    for (int i = 0; i < kFinal; i++) {
+        const int e = off + i;
+        const int ic = e / TK, ik = e - ic * TK;
+        if (i < size && c0 + ic < Cg && k0 + ik < Cg)
+            out[((size_t)(c0 + ic) * Cg + (k0 + ik)) * K + t] = acc[i];
     }
 }
 
@@ -252,19 +261,18 @@ int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y
     BwdWeightParams p{};
     p.dx = dx; p.y = y; p.partial = (float *)workspace;
     p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW; p.Cg = g.Cg;
-    p.nt = pl.nt; p.items = pl.items; p.per_warp = pl.per_warp; p.per_chunk = pl.per_chunk;
+    p.ntk = pl.ntk; p.items = pl.items; p.per_chunk = pl.per_chunk;
     p.nbuf = pl.nbuf; p.XN = pl.XN;
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) ? 1 : 0;
     if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
     dim3 grid(pl.nchunks, g.groups, pl.nz);
-    void (*kern)(const BwdWeightParams) = bwd_weight_partial_kernel<4>;
-    switch (pl.per_warp) {
-        case 1: kern = bwd_weight_partial_kernel<1>; break;
-        case 2: kern = bwd_weight_partial_kernel<2>; break;
-        case 3: kern = bwd_weight_partial_kernel<3>; break;
-        default: break;
-    }
+    void (*kern)(const BwdWeightParams) = nullptr;
+    if (pl.tc == 4 && pl.tk == 12) kern = bwd_weight_partial_kernel<4, 12>;
+    else if (pl.tc == 4 && pl.tk == 8) kern = bwd_weight_partial_kernel<4, 8>;
+    else if (pl.tc == 4 && pl.tk == 4) kern = bwd_weight_partial_kernel<4, 4>;
+    else if (pl.tc == 2) kern = bwd_weight_partial_kernel<2, 2>;
+    else kern = bwd_weight_partial_kernel<1, 1>;
     if (pl.smem_bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
         if (e != cudaSuccess) return (int)e;

@@ -225,6 +225,7 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0) ? 1 : 0;
     if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
+    p.walign = ((uintptr_t)prep_dir % 16 == 0) ? 1 : 0;
     switch (c.vec) {
         case 1: return launch_solve_vec1(c.cc, c.nv, p, grid, c.threads, c.smem_bytes, s);
         case 2: return launch_solve_vec2(c.cc, c.nv, p, grid, c.threads, c.smem_bytes, s);

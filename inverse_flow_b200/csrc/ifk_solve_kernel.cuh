@@ -41,6 +41,7 @@ struct SolveParams {
     int nwork;          // threads that walk the wavefront (multiple of 32); the rest only help staging
     int reverse;
     int bulk;           // image size / pointers allow TMA bulk copies (16-byte granularity)
+    int walign;         // prepared weights are 16-byte aligned (128-bit weight loads allowed)
     long long *probe;   // tuning aid: clock64() stamps of CTA (0,0) thread 0, or nullptr
 };
 
@@ -277,14 +278,28 @@ solve_smem_kernel(const SolveParams p)
         offs[j] = valid ? tbl_off[v] : 0;          // padding entries: weight 0, reads finite data
         const int wcol = valid ? tbl_w[v] : 0;
         const int ci0 = valid ? wcol % Cg : 0;
-#pragma unroll
-        for (int e = 0; e < VEC; e++)
+        if (VEC == 4 && (Cg & 3) == 0 && p.walign) {
+            // 4 consecutive input channels of one tap: one 128-bit load per output channel
 #pragma unroll
             for (int cc = 0; cc < CC; cc++) {
                 const int co = ct * CC + cc;
-                wreg[cc][j * VEC + e] = (valid && co < Cg && ci0 + e < Cg)
-                                            ? __ldg(wg + (size_t)co * p.KDP + Cg + wcol + e) : 0.f;
+                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && co < Cg) w4 = __ldg(reinterpret_cast<const float4 *>(wg + (size_t)co * p.KDP + Cg + wcol));
+                wreg[cc][j * VEC + 0] = w4.x;
+                wreg[cc][j * VEC + 1 % VEC] = w4.y;
+                wreg[cc][j * VEC + 2 % VEC] = w4.z;
+                wreg[cc][j * VEC + 3 % VEC] = w4.w;
             }
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; e++)
+#pragma unroll
+                for (int cc = 0; cc < CC; cc++) {
+                    const int co = ct * CC + cc;
+                    wreg[cc][j * VEC + e] = (valid && co < Cg && ci0 + e < Cg)
+                                                ? __ldg(wg + (size_t)co * p.KDP + Cg + wcol + e) : 0.f;
+                }
+        }
     }
 
     // which of the tile's CC output channels this lane finishes after the reduce-scatter
@@ -360,51 +375,79 @@ solve_smem_kernel(const SolveParams p)
             bulk_load(xbuf, in0 + (size_t)b_next * img_stride, img_bytes, bar);
         }
 
-        // wavefront.  Row `h0 + it*nslots` of this thread meets diagonal d at column d - h; all
-        // addresses advance by a constant per diagonal, so the loop body is loads, FMAs,
-        // shuffles and stores with a handful of integer instructions.
+        // wavefront.  Row `slot + it*nslots` of this thread meets diagonal d at column d - row; all
+        // addresses advance by a constant per diagonal, so a step is loads, FMAs, shuffles and
+        // stores.  Branches are what an otherwise empty step costs (~150 cycles with the generic
+        // loop nest, measured), hence the three specialised loops below.
         IFK_PROBE(5);
-        uint32_t pix_d = pix0, z_d = z0;
-        if (tid < nwork)                         // helper warps skip the wavefront altogether
-        for (int d = 0; d < ndiag; d++) {
-            uint32_t pix = pix_d, za = z_d;
-            int col = d - slot_r;               // column of this thread's row `it` on diagonal d
-#pragma unroll 1
-            for (int it = 0; it < iters; it++, pix += pix_row, za += z_row, col -= nslots) {
-                const bool active = row_ok > it && (unsigned)col < (unsigned)Wr;
-                if (!__any_sync(0xffffffffu, active)) continue;        // warp-uniform
-                const uint32_t pa = active ? pix : ybase;              // idle lanes: a legal pixel
+        auto step = [&](uint32_t pix, uint32_t za, bool active) {
+            const uint32_t pa = active ? pix : ybase;              // idle lanes: a legal pixel
+            float v[NV * VEC];
+#pragma unroll
+            for (int j = 0; j < NV; j++) lds_vec<VEC>(v + j * VEC, pa + (uint32_t)offs[j]);
+            float zv[CC];
+#pragma unroll
+            for (int i = 0; i < CC; i++) zv[i] = (active && i < own_size) ? lds_f32(za + zstride * i) : 0.f;
 
-                float v[NV * VEC];
+            constexpr int NACC = CC >= 4 ? 1 : (CC >= 2 ? 2 : 4);  // independent FMA chains
+            float part[NACC][CC];
 #pragma unroll
-                for (int j = 0; j < NV; j++) lds_vec<VEC>(v + j * VEC, pa + (uint32_t)offs[j]);
-                float zv[CC];
+            for (int a = 0; a < NACC; a++)
 #pragma unroll
-                for (int i = 0; i < CC; i++) zv[i] = (active && i < own_size) ? lds_f32(za + zstride * i) : 0.f;
-
-                constexpr int NACC = CC >= 4 ? 1 : (CC >= 2 ? 2 : 4);  // independent FMA chains
-                float part[NACC][CC];
+                for (int cc = 0; cc < CC; cc++) part[a][cc] = 0.f;
 #pragma unroll
-                for (int a = 0; a < NACC; a++)
+            for (int i = 0; i < NV * VEC; i++)
 #pragma unroll
-                    for (int cc = 0; cc < CC; cc++) part[a][cc] = 0.f;
+                for (int cc = 0; cc < CC; cc++) part[i % NACC][cc] = fmaf(wreg[cc][i], v[i], part[i % NACC][cc]);
+            float acc[CC];
 #pragma unroll
-                for (int i = 0; i < NV * VEC; i++)
+            for (int cc = 0; cc < CC; cc++) {
+                acc[cc] = part[0][cc];
 #pragma unroll
-                    for (int cc = 0; cc < CC; cc++) part[i % NACC][cc] = fmaf(wreg[cc][i], v[i], part[i % NACC][cc]);
-                float acc[CC];
-#pragma unroll
-                for (int cc = 0; cc < CC; cc++) {
-                    acc[cc] = part[0][cc];
-#pragma unroll
-                    for (int a = 1; a < NACC; a++) acc[cc] += part[a][cc];
-                }
-                Rs<CC, 5>::run(acc, zv, ks, NSr, own_size, active, pa + own_c0_bytes, za, zstride);
+                for (int a = 1; a < NACC; a++) acc[cc] += part[a][cc];
             }
-            pix_d += pix_step;
-            z_d += z_step;
-            if (nwork <= 32) __syncwarp();
-            else asm volatile("bar.sync 1, %0;" ::"r"(nwork) : "memory");     // worker warps only
+            Rs<CC, 5>::run(acc, zv, ks, NSr, own_size, active, pa + own_c0_bytes, za, zstride);
+        };
+
+        if (tid < nwork) {                       // helper warps skip the wavefront altogether
+            uint32_t pix_d = pix0, z_d = z0;
+            if (iters == 1 && nwork <= 32) {
+                // one warp, one row per thread: every diagonal has a live row, no block barrier
+                const unsigned row_live = row_ok > 0 ? (unsigned)Wr : 0u;
+                int col = -slot_r;
+#pragma unroll 2
+                for (int d = 0; d < ndiag; d++, col++, pix_d += pix_step, z_d += z_step) {
+                    step(pix_d, z_d, (unsigned)col < row_live);
+                    __syncwarp();
+                }
+            } else if (iters == 1) {
+                // several warps, one row per thread: a warp whose rows are all off the front only
+                // meets the others at the barrier
+                const unsigned row_live = row_ok > 0 ? (unsigned)Wr : 0u;
+                const int wfirst = __shfl_sync(0xffffffffu, slot_r, 0);       // rows of this warp
+                const int wlast = __shfl_sync(0xffffffffu, slot_r, 31);
+                const int d_on = wfirst, d_off = wlast + Wr;                  // live for d in [d_on, d_off)
+                int col = -slot_r;
+                for (int d = 0; d < ndiag; d++, col++, pix_d += pix_step, z_d += z_step) {
+                    if (d >= d_on && d < d_off) step(pix_d, z_d, (unsigned)col < row_live);
+                    asm volatile("bar.sync 1, %0;" ::"r"(nwork) : "memory");  // worker warps only
+                }
+            } else {
+                for (int d = 0; d < ndiag; d++) {
+                    uint32_t pix = pix_d, za = z_d;
+                    int col = d - slot_r;           // column of this thread's row `it` on diagonal d
+#pragma unroll 1
+                    for (int it = 0; it < iters; it++, pix += pix_row, za += z_row, col -= nslots) {
+                        const bool active = row_ok > it && (unsigned)col < (unsigned)Wr;
+                        if (!__any_sync(0xffffffffu, active)) continue;        // warp-uniform
+                        step(pix, za, active);
+                    }
+                    pix_d += pix_step;
+                    z_d += z_step;
+                    if (nwork <= 32) __syncwarp();
+                    else asm volatile("bar.sync 1, %0;" ::"r"(nwork) : "memory");
+                }
+            }
         }
 
         IFK_PROBE(6);
