@@ -62,3 +62,19 @@ def test_unit_requires_multiple_of_four_channels():
 def test_non_square_layer_is_refused():
     with pytest.raises(ValueError):
         inv_flow_no_pad(4, 8, (3, 3))
+
+
+def test_if_glow_model_structure():
+    from inverse_flow_b200 import glow
+    model, shape, batch = glow.build("if_glow_mnist", coupling_width=16, groups=1)
+    assert shape == (1, 28, 28) and batch == 100
+    assert len(model.inv_layers) == 32
+    assert [l.in_channels for l in model.inv_layers[:16]] == [4] * 16
+    assert [l.in_channels for l in model.inv_layers[16:]] == [8] * 16      # split prior halves 16 -> 8... 4*4/2
+    x = torch.randn(2, 8, 4, 4)
+    sq = glow.Squeeze()
+    y, _ = sq(x)
+    assert y.shape == (2, 32, 2, 2) and torch.equal(sq.reverse(y), x)
+    c = glow.Coupling(8, 16)
+    yc, ld = c(torch.randn(2, 8, 4, 4))
+    assert ld.shape == (2,)

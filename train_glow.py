@@ -1,0 +1,107 @@
+"""if_glow training throughput on synthetic data.
+
+    python train_glow.py [--model if_glow_mnist|if_glow_cifar|if_glow_imagenet32] [--steps K] [--warmup W]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P train_glow.py --model if_glow_imagenet32
+
+One process per GPU; the batch is sharded over the ranks (weak scaling: the per-GPU batch is the
+model's batch size) and the only communication is DistributedDataParallel's NCCL all-reduce of the
+gradient buckets -- replacing the reference's single-process nn.DataParallel
+(inf/if_multiGPU_imagenet32.py:410-411).  A step = forward (inverse-conv layers through the
+sm_100a kernels), loss, backward, gradient clipping, Adam update, as in the reference loop
+(inf/train/experiment.py:272-311) minus its per-layer print and parameter clamping.  Prints one
+JSON line (rank 0): images/s of the whole job, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="if_glow_mnist")
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--coupling-width", type=int, default=128)
+    ap.add_argument("--groups", type=int, default=1)
+    args = ap.parse_args()
+
+    from inverse_flow_b200 import glow
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    torch.manual_seed(0)                       # same initial weights on every rank
+    model, shape, batch = glow.build(args.model, args.coupling_width, args.groups or None)
+    model = model.to(device)
+    init_gen = torch.Generator(device=device).manual_seed(99)                 # same batch on every rank
+    model.initialize(torch.rand((batch, *shape), generator=init_gen, device=device) - 0.5)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+
+    def batch_of_images():
+        x = torch.randint(0, 256, (batch, *shape), generator=gen, device=device).float()
+        x = (x + torch.rand(x.shape, generator=gen, device=device)) / 256.0 - 0.5        # dequantise, centre
+        return x
+
+    def step():
+        x = batch_of_images()
+        opt.zero_grad(set_to_none=True)
+        latents, logp = net(x)
+        loss = -logp.mean() / (0.6931471805599453 * x[0].numel())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    losses = []
+    for _ in range(max(args.warmup, 3)):
+        losses.append(float(step()))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    losses.append(float(loss))
+    if rank == 0:
+        n_inv = len(model.inv_layers)
+        print(json.dumps({
+            "metric": "if_glow train images/s", "unit": "images/s", "value": batch * world * args.steps / (ms * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+            "config": {"model": args.model, "input": list(shape), "batch_per_gpu": batch, "inv_conv_layers": n_inv,
+                       "coupling_width": args.coupling_width, "groups": args.groups,
+                       "parameters": sum(p.numel() for p in model.parameters()),
+                       "parallelism": "DistributedDataParallel over NCCL, one process per GPU" if world > 1 else "single GPU",
+                       "note": "eager PyTorch around the inverse-conv kernels; the surrounding layers are minimal "
+                               "stand-ins (out of scope), so this is a drop-in / scaling check, not a tuned number"},
+            "loss_bits_per_dim_first_last": [losses[0], losses[-1]],
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
