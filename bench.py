@@ -249,6 +249,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("IFK_NCCL_DEBUG", "WARN")   # keep stdout to ONE JSON line
         dist.init_process_group("nccl", device_id=device)
     n_gpus = world
 

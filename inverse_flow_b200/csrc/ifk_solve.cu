@@ -113,8 +113,7 @@ static SolveConfig choose_config(const Geometry &g)
         if (((PS / vec) & 1) == 0) PS += vec;      // odd stride in vector units: fewer bank conflicts
         const int NVT = (g.K - 1) * CgV;
         const int YN = round_up(HP * WP * PS, 4);
-        const size_t smem_bytes = 16 + (size_t)2 * round_up(NVT, 4) * sizeof(int) +
-                                  ((size_t)(g.Cg > 1 ? g.Cg * CgP4 : 0) + (size_t)nx * XN + YN) * sizeof(float);
+        const size_t smem_bytes = 16 + ((size_t)(g.Cg > 1 ? g.Cg * CgP4 : 0) + (size_t)nx * XN + YN) * sizeof(float);
         if (smem_bytes > (size_t)kMaxSmemBytes) continue;
         const double lane_waste = (double)(CgV * vec) / g.Cg;     // padded channels still cost FMAs
         static const int kCCs[] = {1, 2, 3, 4, 6, 8, 12};
@@ -222,6 +221,8 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
     }
     p.WP = c.WP; p.PS = c.PS; p.YN = c.YN; p.XN = c.XN; p.CgV = c.CgV; p.NVT = c.NVT; p.CgP4 = c.CgP4;
     p.NS = c.ns; p.NCT = c.nct; p.nslots = c.nslots; p.iters = c.iters; p.nwork = c.nwork;
+    p.kw_magic = (65536 + g.KW - 1) / g.KW;
+    p.v_dt = c.ns / c.CgV; p.v_dq = c.ns % c.CgV;
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0) ? 1 : 0;
     if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;

@@ -37,6 +37,8 @@ struct SolveParams {
     int CgV;            // channel vectors per pixel = ceil(Cg / VEC)
     int NVT;            // (K - 1) * CgV : vector entries of one output row's reduction
     int CgP4;           // Cg rounded up to 4 (row stride of the transposed T in smem)
+    int kw_magic;       // ceil(65536 / KW): t / KW == (t * kw_magic) >> 16 for every tap index
+    int v_dt, v_dq;     // NS / CgV and NS % CgV: how a thread's vector index advances per j
     int NS, NCT, nslots, iters;
     int nwork;          // threads that walk the wavefront (multiple of 32); the rest only help staging
     int reverse;
@@ -211,10 +213,7 @@ solve_smem_kernel(const SolveParams p)
 
     // shared memory carve-up (every region a multiple of 16 bytes)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);         // 16 bytes reserved
-    int *tbl_off = reinterpret_cast<int *>(smem + 4);           // [NVT] byte offset of a vector entry
-    const int tbl_n = (p.NVT + 3) & ~3;
-    int *tbl_w = tbl_off + tbl_n;                               // [NVT] weight column of its 1st channel
-    float *tT = reinterpret_cast<float *>(tbl_w + tbl_n);       // [Cg][CgP4] transposed T
+    float *tT = smem + 4;                                       // [Cg][CgP4] transposed T
     float *xbuf = tT + (Cg > 1 ? Cg * p.CgP4 : 0);              // [Cg][HW] raw input
     float *zbuf = Cg > 1 ? xbuf + p.XN : xbuf;                  // [Cg][HW] T x, then y in place
     float *ybuf = zbuf + p.XN;                                  // [HP][WP][PS] y, zero halo top/left
@@ -232,13 +231,6 @@ solve_smem_kernel(const SolveParams p)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) smem[2] = 0.f;          // source of the opaque zero used by Hold (see above)
 
-    // tables: where a vector entry lives relative to the pixel, and which weights it meets
-    for (int v = tid; v < p.NVT; v += nthr) {
-        const int t = 1 + v / p.CgV, q = v - (t - 1) * p.CgV;
-        const int qh = t / p.KW, qw = t - qh * p.KW;
-        tbl_off[v] = ((-qh * WP - qw) * PS + q * VEC) * 4;
-        tbl_w[v] = (t - 1) * Cg + q * VEC;
-    }
     // ybuf starts from zero for every image: the halo, and the not-yet-written interior that
     // zero-weight padding entries may touch
     for (int i = tid * 4; i < p.YN; i += nthr * 4)
@@ -254,14 +246,6 @@ solve_smem_kernel(const SolveParams p)
             bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
         }
     }
-    if (Cg > 1)
-        for (int i = tid; i < Cg * p.CgP4; i += nthr) {
-            const int ci = i / p.CgP4, co = i - ci * p.CgP4;
-            tT[i] = co < Cg ? __ldg(wg + (size_t)co * p.KDP + ci) : 0.f;
-        }
-    __syncthreads();        // tables + mbarrier init visible
-    IFK_PROBE(1);
-
     const int NS = p.NS, NCT = p.NCT;
     const int ks = tid % NS;
     const int ct = (tid / NS) % NCT;
@@ -271,13 +255,19 @@ solve_smem_kernel(const SolveParams p)
     // this thread's slice of the prepared kernel -> registers, for the whole batch stripe
     float wreg[CC][NV * VEC];
     int offs[NV];
+    // vector entry v = j*NS + ks -> (tap t1+1, channel vector q); advanced without divisions
+    int t1 = ks / p.CgV, q = ks - t1 * p.CgV;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const int v = j * NS + ks;
-        const bool valid = worker && v < p.NVT;
-        offs[j] = valid ? tbl_off[v] : 0;          // padding entries: weight 0, reads finite data
-        const int wcol = valid ? tbl_w[v] : 0;
-        const int ci0 = valid ? wcol % Cg : 0;
+        const bool valid = worker && j * NS + ks < p.NVT;
+        const int t = t1 + 1;
+        const int qh = (t * p.kw_magic) >> 16, qw = t - qh * p.KW;
+        offs[j] = valid ? ((-qh * WP - qw) * PS + q * VEC) * 4 : 0;   // padding entries: weight 0, finite data
+        const int wcol = valid ? t1 * Cg + q * VEC : 0;               // weight column of its 1st channel
+        const int ci0 = valid ? q * VEC : 0;
+        q += p.v_dq;
+        t1 += p.v_dt;
+        if (q >= p.CgV) { q -= p.CgV; t1++; }
         if (VEC == 4 && (Cg & 3) == 0 && p.walign) {
             // 4 consecutive input channels of one tap: one 128-bit load per output channel
 #pragma unroll
@@ -301,6 +291,14 @@ solve_smem_kernel(const SolveParams p)
                 }
         }
     }
+
+    if (Cg > 1)
+        for (int i = tid; i < Cg * p.CgP4; i += nthr) {
+            const int ci = i / p.CgP4, co = i - ci * p.CgP4;
+            tT[i] = co < Cg ? __ldg(wg + (size_t)co * p.KDP + ci) : 0.f;
+        }
+    __syncthreads();        // T, mbarrier init, Hold's zero visible
+    IFK_PROBE(1);
 
     // which of the tile's CC output channels this lane finishes after the reduce-scatter
     int own_off, own_size;

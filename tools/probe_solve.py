@@ -11,8 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from inverse_flow_b200 import _native, functional as IF  # noqa: E402
 from inverse_flow_b200.stack import reference_init_weight  # noqa: E402
 
-NAMES = ["start->tables", "tables->weights", "weights->ybuf0", "ybuf0->image landed", "landed->prepass done",
-         "prepass->(loop start)", "diagonal loop", "loop->store issued", "store read wait"]
+NAMES = ["start -> weights/T loaded, sync", "owner bookkeeping", "loop constants", "wait for the image (TMA)",
+         "pre-pass z = T x", "diagonal loop", "ybuf re-zero / store issue", "store read wait"]
 
 
 def main():
@@ -37,7 +37,7 @@ def main():
     order = [0, 1, 2, 3, 4, 5, 6, 7, 8]
     ndiag = H + W - 1
     for a, b_, name in zip(order[:-1], order[1:], NAMES):
-        print("%-26s %8d cycles" % (name, t[b_] - t[a]))
+        print("%-34s %8d cycles" % (name, t[b_] - t[a]))
     print("total %d cycles; %.1f cycles per diagonal (%d diagonals)" % (t[8] - t[0], (t[6] - t[5]) / ndiag, ndiag))
 
 

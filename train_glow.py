@@ -41,6 +41,7 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("IFK_NCCL_DEBUG", "WARN")   # keep stdout to ONE JSON line
         dist.init_process_group("nccl", device_id=device)
 
     torch.manual_seed(0)                       # same initial weights on every rank
