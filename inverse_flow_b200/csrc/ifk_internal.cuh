@@ -38,6 +38,10 @@ int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y
 int launch_bwd_weight_reduce(const Geometry &g, int count, const void *workspace, size_t workspace_stride,
                              float *dw, size_t dw_stride, cudaStream_t s);
 int describe_solve(const Geometry &g, char *buf, size_t buflen);
+bool stream_solve_available(const Geometry &g);
+int describe_stream_solve(const Geometry &g, char *buf, size_t buflen);
+int launch_solve_stream(const Geometry &g, const float *in, const float *prep_dir, float *out, bool reverse,
+                        cudaStream_t s);
 void set_solve_probe(long long *device_buffer);
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }

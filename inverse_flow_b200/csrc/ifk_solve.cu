@@ -94,8 +94,9 @@ static SolveConfig choose_config(const Geometry &g)
     best.threads = 512;
     best.grid_x = g.B < 4 * kNumSM ? g.B : 4 * kNumSM;
     if (best.grid_x < 1) best.grid_x = 1;
-    const char *force_global = getenv("IFK_SOLVE_GLOBAL");
-    if (force_global && force_global[0] == '1') return best;
+    const char *force_global = getenv("IFK_SOLVE_GLOBAL");      // testing: the plain fallback kernel
+    const char *force_stream = getenv("IFK_SOLVE_STREAM");      // testing: the stream kernel
+    if ((force_global && force_global[0] == '1') || (force_stream && force_stream[0] == '1')) return best;
 
     const int HP = g.H + g.KH - 1, WP = g.W + g.KW - 1;
     const int XN = round_up(g.Cg * g.H * g.W, 4);
@@ -216,6 +217,9 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
     p.probe = g_probe;
     dim3 grid(c.grid_x, g.groups);
     if (!c.smem) {
+        const char *force_global = getenv("IFK_SOLVE_GLOBAL");
+        if (!(force_global && force_global[0] == '1') && stream_solve_available(g))
+            return launch_solve_stream(g, in, prep_dir, out, reverse, s);
         solve_global_kernel<<<grid, c.threads, 0, s>>>(p);
         return cuda_status(cudaGetLastError());
     }
@@ -241,8 +245,12 @@ int describe_solve(const Geometry &g, char *buf, size_t buflen)
     if (c.smem)
         snprintf(buf, buflen, "smem<cc=%d,nv=%d,vec=%d> ns=%d nct=%d slots=%d iters=%d threads=%d(%d) smem=%zuB grid=%dx%d",
                  c.cc, c.nv, c.vec, c.ns, c.nct, c.nslots, c.iters, c.threads, c.nwork, c.smem_bytes, c.grid_x, g.groups);
-    else
+    else {
+        const char *force_global = getenv("IFK_SOLVE_GLOBAL");
+        if (!(force_global && force_global[0] == '1') && stream_solve_available(g))
+            return describe_stream_solve(g, buf, buflen);
         snprintf(buf, buflen, "global threads=%d grid=%dx%d", c.threads, c.grid_x, g.groups);
+    }
     return 0;
 }
 

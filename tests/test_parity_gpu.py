@@ -128,8 +128,37 @@ def test_global_fallback_kernel(IF, shape, monkeypatch):
     assert_parity(run_all(IF, x, w, g, groups))
 
 
+@pytest.mark.parametrize("shape", [(3, 12, 16, 16, 3, 3, 1, 0.02), (2, 8, 7, 7, 2, 2, 4, 0.05),
+                                   (2, 3, 9, 13, 3, 3, 1, 0.1), (2, 5, 13, 9, 2, 3, 1, 0.1),
+                                   (2, 24, 8, 8, 3, 3, 1, 0.02), (2, 4, 6, 6, 5, 5, 1, 0.02)],
+                         ids=lambda s: "x".join(map(str, s[:7])))
+def test_stream_kernel(IF, shape, monkeypatch):
+    """Force the kernel for images that exceed shared memory (reads neighbours back from the output)."""
+    monkeypatch.setenv("IFK_SOLVE_STREAM", "1")
+    from inverse_flow_b200 import _native
+    B, C, H, W, KH, KW, groups, scale = shape
+    assert _native.describe_solve(_native.problem(B, C, H, W, KH, KW, C, groups)).startswith("stream<")
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, KH, KW, scale)
+    assert_parity(run_all(IF, x, w, g, groups))
+
+
+def test_large_images_take_the_stream_path(IF):
+    """(2,12,64,64) k=3 and (2,48,32,32) k=3 exceed shared memory: stream kernel; dW staged or not."""
+    from inverse_flow_b200 import _native
+    for (B, C, H, W, k, scale) in [(2, 12, 64, 64, 3, 0.01), (2, 48, 32, 32, 3, 0.005)]:
+        assert _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1)).startswith("stream<")
+        rng = np.random.default_rng(6)
+        x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        w = make_weight(rng, C, C, k, k, scale)
+        assert_parity(run_all(IF, x, w, g, 1))
+
+
 def test_large_image_takes_the_global_path(IF):
-    """(2, 48, 32, 32) k=5 does not fit in shared memory (and dW runs unstaged)."""
+    """(2, 48, 32, 32) k=5: neither shared memory nor the register file holds it -> plain fallback."""
     rng = np.random.default_rng(5)
     B, C, H, W, k = 2, 48, 32, 32, 5
     x = rng.standard_normal((B, C, H, W)).astype(np.float32)
