@@ -27,6 +27,7 @@ struct BwdWeightPlan {
     int nchunks;       // batch chunks (== partial buffers)
     int per_chunk;     // images per chunk
     int nbuf;          // 2: double buffered, 1: single, 0: images read from global memory
+    int nstage;        // images staged per buffer (small images travel in batches)
     int CgP;           // channels padded to the tile sizes (padding rows stay zero in smem)
     int XN;            // floats per staged image (16-byte multiple)
     size_t smem_bytes;
@@ -52,7 +53,18 @@ static BwdWeightPlan make_plan(const Geometry &g)
     const size_t one = (size_t)2 * pl.XN * sizeof(float);          // dX + y of one image
     pl.nbuf = 2 * one + 64 <= (size_t)kMaxSmemBytes ? 2 : (one + 64 <= (size_t)kMaxSmemBytes ? 1 : 0);
     if (pl.per_chunk == 1 && pl.nbuf == 2) pl.nbuf = 1;
-    pl.smem_bytes = pl.nbuf ? 64 + pl.nbuf * one : 0;
+    // small images: several per buffer, so that one TMA round trip feeds many pixel steps
+    pl.nstage = 1;
+    if (pl.nbuf) {
+        const size_t budget = 96 * 1024;                           // per buffer
+        int n = (int)(budget / one);
+        if (n < 1) n = 1;
+        if (n > 16) n = 16;
+        const int need = (pl.per_chunk + pl.nbuf - 1) / pl.nbuf;   // no point staging more than this
+        if (n > need) n = need > 0 ? need : 1;
+        pl.nstage = n;
+    }
+    pl.smem_bytes = pl.nbuf ? 64 + (size_t)pl.nbuf * pl.nstage * one : 0;
     return pl;
 }
 
@@ -65,7 +77,7 @@ size_t bwd_weight_workspace_bytes(const Geometry &g)
 struct BwdWeightParams {
     const float *dx, *y;
     float *partial;
-    int B, C, H, W, KH, KW, Cg, ntk, items, per_chunk, nbuf, XN, bulk;
+    int B, C, H, W, KH, KW, Cg, ntk, items, per_chunk, nbuf, nstage, XN, bulk;
 };
 
 // sum N per-lane values over the 32 lanes by recursive halving: N/2 + N/4 + ... shuffles
@@ -120,63 +132,79 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
     const float *dx0 = p.dx + (size_t)G * Cg * HW, *y0 = p.y + (size_t)G * Cg * HW;
     const uint32_t img_bytes = (uint32_t)(Cg * HW) * 4u;
     const bool staged = p.nbuf > 0, bulk = staged && p.bulk;
+    const int XN = p.XN, nstage = p.nstage;
+    const size_t buf_floats = (size_t)2 * nstage * XN;            // one buffer: nstage x (dX, y)
+
+    // stage `n` images starting at image b into buffer `which` (thread 0; TMA bulk copies)
+    auto issue = [&](int which, int b, int n) {
+        float *bufw = buf0 + (size_t)which * buf_floats;
+        mbar_expect_tx(&bars[which], 2u * img_bytes * (uint32_t)n);
+        for (int i = 0; i < n; i++) {
+            bulk_load(bufw + (size_t)(2 * i) * XN, dx0 + (size_t)(b + i) * img_stride, img_bytes, &bars[which]);
+            bulk_load(bufw + (size_t)(2 * i + 1) * XN, y0 + (size_t)(b + i) * img_stride, img_bytes, &bars[which]);
+        }
+    };
 
     if (bulk && tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
-        mbar_expect_tx(&bars[0], 2 * img_bytes);
-        bulk_load(buf0, dx0 + (size_t)b_begin * img_stride, img_bytes, &bars[0]);
-        bulk_load(buf0 + p.XN, y0 + (size_t)b_begin * img_stride, img_bytes, &bars[0]);
+        const int n0 = b_end - b_begin < nstage ? b_end - b_begin : nstage;
+        issue(0, b_begin, n0);
     }
     if (staged) {       // channels padded up to the tile are zero for good (bulk copies never touch them)
-        for (int bsel = 0; bsel < 2 * p.nbuf; bsel++)
-            for (int i = Cg * HW + tid; i < p.XN; i += blockDim.x) buf0[(size_t)bsel * p.XN + i] = 0.f;
+        for (int bsel = 0; bsel < 2 * p.nbuf * nstage; bsel++)
+            for (int i = Cg * HW + tid; i < XN; i += blockDim.x) buf0[(size_t)bsel * XN + i] = 0.f;
     }
     __syncthreads();
     uint32_t parity0 = 0u, parity1 = 0u;
 
-    for (int b = b_begin; b < b_end; b++) {
-        const int cur = p.nbuf == 2 ? (b - b_begin) & 1 : 0;
-        const float *dxs, *ys;
+    int stage_idx = 0;
+    for (int b = b_begin; b < b_end; b += nstage, stage_idx++) {
+        const int n_img = b_end - b < nstage ? b_end - b : nstage;
+        const int cur = p.nbuf == 2 ? stage_idx & 1 : 0;
+        const float *stage_base;
         if (staged) {
-            float *bufc = buf0 + (size_t)cur * 2 * p.XN;
+            float *bufc = buf0 + (size_t)cur * buf_floats;
             if (bulk) {
-                if (p.nbuf == 2 && b + 1 < b_end && tid == 0) {          // prefetch into the other buffer
-                    float *bufn = buf0 + (size_t)(cur ^ 1) * 2 * p.XN;   // (its readers passed the barrier below)
-                    mbar_expect_tx(&bars[cur ^ 1], 2 * img_bytes);
-                    bulk_load(bufn, dx0 + (size_t)(b + 1) * img_stride, img_bytes, &bars[cur ^ 1]);
-                    bulk_load(bufn + p.XN, y0 + (size_t)(b + 1) * img_stride, img_bytes, &bars[cur ^ 1]);
-                }
+                const int b_nx = b + nstage;
+                if (p.nbuf == 2 && b_nx < b_end && tid == 0)             // prefetch the next stage
+                    issue(cur ^ 1, b_nx, b_end - b_nx < nstage ? b_end - b_nx : nstage);
                 mbar_wait(&bars[cur], cur ? parity1 : parity0);
                 if (cur) parity1 ^= 1u; else parity0 ^= 1u;
             } else {
                 __syncthreads();
-                const float *sd = dx0 + (size_t)b * img_stride, *sy = y0 + (size_t)b * img_stride;
-                for (int i = tid; i < Cg * HW; i += blockDim.x) {
-                    bufc[i] = __ldg(sd + i);
-                    bufc[p.XN + i] = __ldg(sy + i);
+                for (int im = 0; im < n_img; im++) {
+                    const float *sd = dx0 + (size_t)(b + im) * img_stride, *sy = y0 + (size_t)(b + im) * img_stride;
+                    for (int i = tid; i < Cg * HW; i += blockDim.x) {
+                        bufc[(size_t)(2 * im) * XN + i] = __ldg(sd + i);
+                        bufc[(size_t)(2 * im + 1) * XN + i] = __ldg(sy + i);
+                    }
                 }
                 __syncthreads();
             }
-            dxs = bufc;
-            ys = bufc + p.XN;
+            stage_base = bufc;
         } else {
-            dxs = dx0 + (size_t)b * img_stride;
-            ys = y0 + (size_t)b * img_stride;
+            stage_base = nullptr;
         }
 
         if (live) {
-            // lanes stride over the pixels: every shared-memory read is 32 consecutive words
-            int h = lane / W, w = lane - h * W;
-            for (int r = lane; r < HW; r += 32) {
+            // lanes stride over the (image, pixel) pairs of the stage: every shared-memory read is
+            // 32 consecutive words, and tiny images still fill the warp
+            int im = 0, h = 0, w = lane;
+            while (w >= W) { w -= W; h++; }
+            while (h >= p.H) { h -= p.H; im++; }
+            while (im < n_img) {
                 if (h >= qh && w >= qw) {
+                    const int r = h * W + w;
                     float a[TC], v[TK];
                     if (staged) {
+                        const float *dxs = stage_base + (size_t)(2 * im) * XN, *ys = dxs + XN;
 #pragma unroll
                         for (int i = 0; i < TC; i++) a[i] = dxs[aoff + i * HW + r];
 #pragma unroll
                         for (int k = 0; k < TK; k++) v[k] = ys[voff + k * HW + r];
                     } else {
+                        const float *dxs = dx0 + (size_t)(b + im) * img_stride, *ys = y0 + (size_t)(b + im) * img_stride;
 #pragma unroll
                         for (int i = 0; i < TC; i++)
                             a[i] = c0 + i < Cg ? __ldg(dxs + aoff + i * HW + r) : 0.f;
@@ -191,15 +219,15 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
                 }
                 w += 32;
                 while (w >= W) { w -= W; h++; }
+                while (h >= p.H) { h -= p.H; im++; }
             }
         }
         if (bulk && p.nbuf == 2) __syncthreads();      // everyone is done with `cur` before it is refilled
-        if (bulk && p.nbuf == 1 && b + 1 < b_end) {
+        if (bulk && p.nbuf == 1 && b + nstage < b_end) {
             __syncthreads();
             if (tid == 0) {
-                mbar_expect_tx(&bars[0], 2 * img_bytes);
-                bulk_load(buf0, dx0 + (size_t)(b + 1) * img_stride, img_bytes, &bars[0]);
-                bulk_load(buf0 + p.XN, y0 + (size_t)(b + 1) * img_stride, img_bytes, &bars[0]);
+                const int b_nx = b + nstage;
+                issue(0, b_nx, b_end - b_nx < nstage ? b_end - b_nx : nstage);
             }
         }
     }
@@ -262,7 +290,7 @@ int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y
     p.dx = dx; p.y = y; p.partial = (float *)workspace;
     p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW; p.Cg = g.Cg;
     p.ntk = pl.ntk; p.items = pl.items; p.per_chunk = pl.per_chunk;
-    p.nbuf = pl.nbuf; p.XN = pl.XN;
+    p.nbuf = pl.nbuf; p.nstage = pl.nstage; p.XN = pl.XN;
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) ? 1 : 0;
     if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
