@@ -1,11 +1,76 @@
 // x = L y : the masked (autoregressive) convolution, sampling direction z -> x.
 // Replaces inv_conv_fwd_cuda_inverse (inv_conv_with_bp_kernel_general.cu:141-264), which
 // walks the anti-diagonals with a launch + device sync each although nothing depends on
-// anything here.  One launch, one thread per output element, coalesced along W; the centre
-// tap is masked to its strictly-lower triangle and the diagonal is the implicit 1.
+// anything here.
+//
+// conv_tiled_kernel: a CTA owns a stripe of images of one channel group.  The group's masked
+// weights are transposed once into shared memory as [tap][ci][co] (centre tap = unit diagonal +
+// strictly-lower triangle, so the mask costs nothing afterwards); a thread owns (pixel, 4
+// output channels) items: per (tap, ci) one coalesced global load of y (neighbouring pixels
+// overlap in L1) and one broadcast 128-bit shared load of 4 weights feed 4 FMAs; the border
+// test is per tap, not per element.
+// conv_kernel: one thread per output, everything through L1/L2 -- used for single-channel and
+// for wide groups (Cg > 16), where staging the weights per CTA costs more than it saves.
 #include "ifk_internal.cuh"
 
 namespace ifk {
+
+__global__ void __launch_bounds__(256)
+conv_tiled_kernel(const float *__restrict__ y, const float *__restrict__ weight, float *__restrict__ x,
+                  int B, int C, int H, int W, int KH, int KW, int Cw, int Cg, int CgP4, int nsplit)
+{
+    extern __shared__ __align__(16) float wT[];              // [K][Cg][CgP4]
+    const int HW = H * W, K = KH * KW;
+    const int G = blockIdx.y, tid = threadIdx.x;
+    const size_t tap_stride = (size_t)K, row_stride = (size_t)Cw * tap_stride;
+    const float *wg = weight + (size_t)G * Cg * row_stride;
+
+    for (int e = tid; e < K * Cg * CgP4; e += blockDim.x) {
+        const int co = e % CgP4, ci = (e / CgP4) % Cg, t = e / (CgP4 * Cg);
+        const int qh = t / KW, qw = t - qh * KW;
+        const int a = (KH - 1 - qh) * KW + (KW - 1 - qw);
+        float v = 0.f;
+        if (co < Cg) {
+            if (t == 0) v = ci < co ? __ldg(wg + co * row_stride + ci * tap_stride + a) : (ci == co ? 1.f : 0.f);
+            else        v = __ldg(wg + co * row_stride + ci * tap_stride + a);
+        }
+        wT[e] = v;
+    }
+    __syncthreads();
+
+    const int nquad = CgP4 >> 2;
+    // work unit = (image, split): the items of one image may be shared by `nsplit` CTAs
+    for (int u = blockIdx.x; u < B * nsplit; u += gridDim.x) {
+        const int b = u / nsplit, sp = u - b * nsplit;
+        const float *yb = y + ((size_t)b * C + (size_t)G * Cg) * HW;
+        float *xb = x + ((size_t)b * C + (size_t)G * Cg) * HW;
+        for (int item = sp * blockDim.x + tid; item < HW * nquad; item += nsplit * blockDim.x) {
+            const int cq = item / HW, r = item - cq * HW;
+            const int h = r / W, w = r - h * W;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const int qh_max = h < KH - 1 ? h : KH - 1, qw_max = w < KW - 1 ? w : KW - 1;
+            for (int qh = 0; qh <= qh_max; qh++)
+                for (int qw = 0; qw <= qw_max; qw++) {
+                    const float *yp = yb + r - qh * W - qw;
+                    const float *wp = wT + (size_t)(qh * KW + qw) * Cg * CgP4 + cq * 4;
+#pragma unroll 4
+                    for (int ci = 0; ci < Cg; ci++) {
+                        const float yv = __ldg(yp + (size_t)ci * HW);
+                        const float4 w4 = *reinterpret_cast<const float4 *>(wp + ci * CgP4);
+                        a0 = fmaf(w4.x, yv, a0);
+                        a1 = fmaf(w4.y, yv, a1);
+                        a2 = fmaf(w4.z, yv, a2);
+                        a3 = fmaf(w4.w, yv, a3);
+                    }
+                }
+            const int co = cq * 4;
+            xb[(size_t)co * HW + r] = a0;
+            if (co + 1 < Cg) xb[(size_t)(co + 1) * HW + r] = a1;
+            if (co + 2 < Cg) xb[(size_t)(co + 2) * HW + r] = a2;
+            if (co + 3 < Cg) xb[(size_t)(co + 3) * HW + r] = a3;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256)
 conv_kernel(const float *__restrict__ y, const float *__restrict__ weight, float *__restrict__ x,
@@ -41,6 +106,29 @@ int launch_conv(const Geometry &g, const float *y, const float *weight, float *x
 {
     const size_t total = (size_t)g.B * g.C * g.H * g.W;
     if (total == 0) return 0;
+    const int CgP4 = round_up(g.Cg, 4);
+    const size_t smem = (size_t)g.K * g.Cg * CgP4 * sizeof(float);
+    if (g.Cg >= 3 && g.Cg <= 16 && smem <= (size_t)kMaxSmemBytes) {      // small groups: weights cheap to stage
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        int per_sm = (int)((size_t)kMaxSmemBytes / (smem + 1024));
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        int grid_x = (kNumSM * per_sm + g.groups - 1) / g.groups;
+        const int items = g.H * g.W * (CgP4 >> 2);
+        int nsplit = (grid_x + g.B - 1) / g.B;                 // fill the GPU when the batch is small
+        const int max_split = (items + 255) / 256;
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit < 1) nsplit = 1;
+        if (grid_x > g.B * nsplit) grid_x = g.B * nsplit;
+        dim3 grid(grid_x, g.groups);
+        conv_tiled_kernel<<<grid, 256, smem, s>>>(y, weight, x, g.B, g.C, g.H, g.W, g.KH, g.KW, g.Cw, g.Cg, CgP4,
+                                                  nsplit);
+        return cuda_status(cudaGetLastError());
+    }
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)kNumSM * 32;
     if (blocks > cap) blocks = cap;
