@@ -41,7 +41,12 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("IFK_NCCL_DEBUG", "WARN")   # keep stdout to ONE JSON line
+        # keep stdout to ONE JSON line: NCCL prints its version banner to stdout at any debug level
+        if "IFK_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["IFK_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     torch.manual_seed(0)                       # same initial weights on every rank
