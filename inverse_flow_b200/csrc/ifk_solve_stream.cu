@@ -7,7 +7,13 @@
 // staged; the pre-pass writes z = T x straight into the OUTPUT tensor, the wavefront reads its
 // neighbours back from the output tensor (L1/L2; the CTA barrier orders its own global writes
 // at CTA scope) and overwrites z with y in place.  No workspace, any H x W; the only limit is
-// that the weight slices fit the register file: Cg*Cg*(K-1) <= ~48K.
+// that the weight slices fit the register file: Cg*Cg*(K-1) <= ~48K per CTA.
+//
+// Cluster mode (CL = true) lifts that limit: a thread-block cluster of 2..8 CTAs shares one
+// image, each CTA owning a slice of the OUTPUT channels (and the registers for its weights);
+// y is exchanged through the output tensor in L2 (ld.global.cg) and the per-diagonal barrier
+// becomes a cluster barrier (barrier.cluster.arrive.release / wait.acquire).  This is what makes
+// Cg = 96 (73.7K weights at k = 3, more than one SM's register file) run at all.
 //
 // Replaces, for large images, the same reference loop as the resident kernel
 // (inv_conv_with_bp_kernel_general.cu:72-129).
@@ -26,6 +32,7 @@ struct StreamParams {
     int NS, NCT, nslots, iters, nwork;
     int kw_magic, v_dt, v_dq;
     int reverse;
+    int csize;          // CTAs per cluster (1 = no cluster); CTA r owns channel tiles [r*NCT, (r+1)*NCT)
 };
 
 // reduce-scatter as Rs (ifk_solve_kernel.cuh), finishing into global memory
@@ -61,7 +68,24 @@ constexpr int stream_max_threads()
     return t > 1024 ? 1024 : t;
 }
 
-template <int CC, int NV>
+__device__ __forceinline__ float ld_cg(const float *p)
+{
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+template <int CC, int NV, bool CL>
 __global__ void __launch_bounds__(stream_max_threads<CC, NV>())
 solve_stream_kernel(const StreamParams p)
 {
@@ -73,7 +97,8 @@ solve_stream_kernel(const StreamParams p)
 
     const int NS = p.NS, NCT = p.NCT;
     const int ks = tid % NS;
-    const int ct = (tid / NS) % NCT;
+    const int crank = CL ? (int)cluster_ctarank() : 0;
+    const int ct = crank * NCT + (tid / NS) % NCT;          // global channel tile of this thread
     const int slot = tid / (NS * NCT);
     const bool worker = slot < p.nslots;
 
@@ -115,14 +140,15 @@ solve_stream_kernel(const StreamParams p)
     const int ndiag = H + W - 1;
     const int KH1 = p.KH - 1, KW1 = p.KW - 1;
 
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const int nclusters = CL ? gridDim.x / p.csize : gridDim.x;
+    for (int b = CL ? blockIdx.x / p.csize : blockIdx.x; b < p.B; b += nclusters) {
         const size_t gbase = ((size_t)b * p.C + (size_t)G * Cg) * HW;
         const float *in_b = p.in + gbase;
         float *out_b = p.out + gbase;
 
         // pre-pass z = T x, pointwise, coalesced over the pixels; z goes straight to the output
         const int n4 = p.CgP4 >> 2;
-        for (int i = tid; i < HW * n4; i += nthr) {
+        for (int i = (CL ? crank * nthr : 0) + tid; i < HW * n4; i += (CL ? p.csize : 1) * nthr) {
             const int c4 = i / HW, r = i - c4 * HW;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             const float *tp = tT + c4 * 4;
@@ -141,9 +167,10 @@ solve_stream_kernel(const StreamParams p)
             if (co + 2 < Cg) out_b[(size_t)(co + 2) * HW + r] = a2;
             if (co + 3 < Cg) out_b[(size_t)(co + 3) * HW + r] = a3;
         }
-        __syncthreads();        // z visible to the whole CTA (barrier = CTA-scope fence)
+        if (CL) cluster_barrier();   // z visible to the whole cluster (release/acquire at cluster scope)
+        else __syncthreads();        // z visible to the whole CTA (barrier = CTA-scope fence)
 
-        if (tid < p.nwork) {
+        if (CL || tid < p.nwork) {       // cluster barriers need every thread of every CTA
             for (int d = 0; d < ndiag; d++) {
                 for (int it = 0; it < p.iters; it++) {
                     const int h = slot + it * p.nslots;
@@ -158,16 +185,16 @@ solve_stream_kernel(const StreamParams p)
                     float v[NV];
                     if (hh >= KH1 && ww >= KW1) {                          // interior: no border tests
 #pragma unroll
-                        for (int j = 0; j < NV; j++) v[j] = base[offs[j]];      // padding: offset 0, weight 0
+                        for (int j = 0; j < NV; j++) v[j] = CL ? ld_cg(base + offs[j]) : base[offs[j]];   // padding: offset 0, weight 0
                     } else {
 #pragma unroll
                         for (int j = 0; j < NV; j++)
-                            v[j] = (hh >= (qhw[j] >> 8) && ww >= (qhw[j] & 0xff)) ? base[offs[j]] : 0.f;
+                            v[j] = (hh >= (qhw[j] >> 8) && ww >= (qhw[j] & 0xff)) ? (CL ? ld_cg(base + offs[j]) : base[offs[j]]) : 0.f;
                     }
                     float zv[CC];
 #pragma unroll
                     for (int i = 0; i < CC; i++)
-                        zv[i] = (active && i < own_size) ? base[(size_t)(own_c0 + i) * HW] : 0.f;
+                        zv[i] = (active && i < own_size) ? (CL ? ld_cg(base + (size_t)(own_c0 + i) * HW) : base[(size_t)(own_c0 + i) * HW]) : 0.f;
 
                     float acc[CC];
 #pragma unroll
@@ -178,10 +205,11 @@ solve_stream_kernel(const StreamParams p)
                         for (int cc = 0; cc < CC; cc++) acc[cc] = fmaf(wreg[cc][j], v[j], acc[cc]);
                     RsGlobal<CC, 5>::run(acc, zv, ks, NS >> 1, own_size, active, base + (size_t)own_c0 * HW, HW);
                 }
-                asm volatile("bar.sync 1, %0;" ::"r"(p.nwork) : "memory");    // worker warps; CTA-scope fence
+                if (CL) cluster_barrier();
+                else asm volatile("bar.sync 1, %0;" ::"r"(p.nwork) : "memory");    // worker warps; CTA-scope fence
             }
         }
-        __syncthreads();
+        if (CL) cluster_barrier(); else __syncthreads();
     }
 }
 
@@ -189,6 +217,7 @@ solve_stream_kernel(const StreamParams p)
 struct StreamConfig {
     bool ok;
     int cc, nv, ns, nct, nslots, iters, threads, nwork, grid_x;
+    int csize;          // CTAs per cluster sharing one image (output-channel split); nct is per CTA
     size_t smem_bytes;
 };
 
@@ -217,30 +246,36 @@ static StreamConfig choose_stream(const Geometry &g)
     if (const char *e = getenv("IFK_STREAM_CFG")) sscanf(e, "%d,%d", &fcc, &fnv);   // tuning only
     static const int kCCs[] = {12, 8, 6, 4, 3, 2, 1};
     static const int kNVs[] = {3, 6, 8, 9, 12, 18, 24};
-    for (int cc : kCCs) {
-        if (cc > g.Cg) continue;
-        const int nct = (g.Cg + cc - 1) / cc;
-        for (int nv : kNVs) {
-            const int tmax = stream_variant_threads(cc, nv);
-            if (tmax == 0) continue;
-            if (fcc && (cc != fcc || nv != fnv)) continue;
-            for (int ns = 1; ns <= 32; ns *= 2) {
-                if ((long)ns * nv < NVT) continue;
-                if (ns > 1 && (long)(ns / 2) * nv >= NVT) continue;
-                const int per_slot = ns * nct;
-                if (per_slot > tmax) continue;
-                int nslots = tmax / per_slot;
-                if (nslots > g.H) nslots = g.H;
-                const int iters = (g.H + nslots - 1) / nslots;
-                const int threads = round_up(nslots * per_slot, 32);
-                // work per diagonal ~ iters * (loads + FMAs + shuffles), all slots in parallel
-                const double waste = (double)(ns * nv) / NVT * (double)(nct * cc) / g.Cg;
-                const double cost = iters * (nv * (2.0 + cc) + 6.0 * cc + 60.0) * waste * ((threads + 127) / 128);
-                if (cost < best_cost) {
-                    best_cost = cost;
-                    best.ok = true;
-                    best.cc = cc; best.nv = nv; best.ns = ns; best.nct = nct; best.nslots = nslots;
-                    best.iters = iters; best.threads = threads; best.nwork = threads;
+    static const int kCsizes[] = {1, 2, 4, 8};
+    for (int csize : kCsizes) {
+        if (best.ok) break;                      // smallest cluster that holds the weights wins
+        for (int cc : kCCs) {
+            if (cc > g.Cg) continue;
+            const int nct_total = (g.Cg + cc - 1) / cc;
+            if (csize > nct_total) continue;
+            const int nct = (nct_total + csize - 1) / csize;
+            for (int nv : kNVs) {
+                const int tmax = stream_variant_threads(cc, nv);
+                if (tmax == 0) continue;
+                if (fcc && (cc != fcc || nv != fnv)) continue;
+                for (int ns = 1; ns <= 32; ns *= 2) {
+                    if ((long)ns * nv < NVT) continue;
+                    if (ns > 1 && (long)(ns / 2) * nv >= NVT) continue;
+                    const int per_slot = ns * nct;
+                    if (per_slot > tmax) continue;
+                    int nslots = tmax / per_slot;
+                    if (nslots > g.H) nslots = g.H;
+                    const int iters = (g.H + nslots - 1) / nslots;
+                    const int threads = round_up(nslots * per_slot, 32);
+                    // work per diagonal ~ iters * (loads + FMAs + shuffles), all slots in parallel
+                    const double waste = (double)(ns * nv) / NVT * (double)(nct * csize * cc) / g.Cg;
+                    const double cost = iters * (nv * (2.0 + cc) + 6.0 * cc + 60.0) * waste * ((threads + 127) / 128);
+                    if (cost < best_cost) {
+                        best_cost = cost;
+                        best.ok = true;
+                        best.cc = cc; best.nv = nv; best.ns = ns; best.nct = nct; best.nslots = nslots;
+                        best.iters = iters; best.threads = threads; best.nwork = threads; best.csize = csize;
+                    }
                 }
             }
         }
@@ -250,10 +285,10 @@ static StreamConfig choose_stream(const Geometry &g)
     int per_sm = 2048 / best.threads;
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
-    int grid_x = (kNumSM * per_sm + g.groups - 1) / g.groups;
-    if (grid_x > g.B) grid_x = g.B;
-    if (grid_x < 1) grid_x = 1;
-    best.grid_x = grid_x;
+    int nclusters = (kNumSM * per_sm / best.csize + g.groups - 1) / g.groups;
+    if (nclusters > g.B) nclusters = g.B;
+    if (nclusters < 1) nclusters = 1;
+    best.grid_x = nclusters * best.csize;
     return best;
 }
 
@@ -262,8 +297,8 @@ bool stream_solve_available(const Geometry &g) { return choose_stream(g).ok; }
 int describe_stream_solve(const Geometry &g, char *buf, size_t buflen)
 {
     const StreamConfig c = choose_stream(g);
-    snprintf(buf, buflen, "stream<cc=%d,nv=%d> ns=%d nct=%d slots=%d iters=%d threads=%d grid=%dx%d",
-             c.cc, c.nv, c.ns, c.nct, c.nslots, c.iters, c.threads, c.grid_x, g.groups);
+    snprintf(buf, buflen, "stream<cc=%d,nv=%d> cluster=%d ns=%d nct=%d slots=%d iters=%d threads=%d grid=%dx%d",
+             c.cc, c.nv, c.csize, c.ns, c.nct, c.nslots, c.iters, c.threads, c.grid_x, g.groups);
     return 0;
 }
 
@@ -281,20 +316,38 @@ int launch_solve_stream(const Geometry &g, const float *in, const float *prep_di
     p.kw_magic = (65536 + g.KW - 1) / g.KW;
     p.v_dt = c.ns / g.Cg; p.v_dq = c.ns % g.Cg;
     p.reverse = reverse ? 1 : 0;
+    p.csize = c.csize;
     dim3 grid(c.grid_x, g.groups);
-#define X(CC, NV)                                                                                         \
-    if (c.cc == CC && c.nv == NV) {                                                                       \
-        auto kern = solve_stream_kernel<CC, NV>;                                                          \
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(c.threads);
+    cfg.dynamicSmemBytes = c.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = c.csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c.csize > 1 ? 1 : 0;
+#define IFK_LAUNCH(KERN)                                                                                  \
+    {                                                                                                     \
+        auto kern = KERN;                                                                                 \
         if (c.smem_bytes > 48 * 1024) {                                                                   \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                                  (int)c.smem_bytes);                                      \
             if (e != cudaSuccess) return (int)e;                                                          \
         }                                                                                                 \
-        kern<<<grid, c.threads, c.smem_bytes, s>>>(p);                                                    \
-        return cuda_status(cudaGetLastError());                                                           \
+        return cuda_status(cudaLaunchKernelEx(&cfg, kern, p));                                            \
+    }
+#define X(CC, NV)                                                                                         \
+    if (c.cc == CC && c.nv == NV) {                                                                       \
+        if (c.csize > 1) IFK_LAUNCH((solve_stream_kernel<CC, NV, true>))                                  \
+        else IFK_LAUNCH((solve_stream_kernel<CC, NV, false>))                                             \
     }
     IFK_STREAM_VARIANTS
 #undef X
+#undef IFK_LAUNCH
     return IFK_ERR_UNSUPPORTED;
 }
 

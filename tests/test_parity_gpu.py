@@ -157,6 +157,19 @@ def test_large_images_take_the_stream_path(IF):
         assert_parity(run_all(IF, x, w, g, 1))
 
 
+def test_wide_group_runs_as_a_thread_block_cluster(IF):
+    """Cg = 96, k = 3: 73.7K prepared weights exceed one SM's register file, so the stream kernel
+    runs as a cluster of CTAs that split the output channels and meet at a cluster barrier."""
+    from inverse_flow_b200 import _native
+    B, C, H, W, k = 2, 96, 8, 8, 3
+    assert "cluster=4" in _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1))
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, k, k, 0.003)
+    assert_parity(run_all(IF, x, w, g, 1))
+
+
 def test_large_image_takes_the_global_path(IF):
     """(2, 48, 32, 32) k=5: neither shared memory nor the register file holds it -> plain fallback."""
     rng = np.random.default_rng(5)
