@@ -88,3 +88,27 @@ def test_describe_solve_picks_the_resident_kernel_for_model_shapes(lib):
         assert d.startswith("smem<"), (shape, d)
     big = _native.describe_solve(_native.problem(8, 96, 64, 64, 7, 7, 96, 1))
     assert big.startswith("global")
+
+
+def test_batched_entry_points_validate_arguments(lib):
+    p = _native.problem(2, 4, 5, 5, 3, 3, 4, 1)
+    dummy = ctypes.c_void_p(16)
+    # count == 0 is a no-op; negative counts and NULL buffers are refused before any launch
+    assert lib.ifk_prepare_many_f32(ctypes.byref(p), 0, None, 0, None, 0, None) == 0
+    assert lib.ifk_prepare_many_f32(ctypes.byref(p), -1, dummy, 0, dummy, 0, None) == -2
+    assert lib.ifk_prepare_many_f32(ctypes.byref(p), 2, None, 0, dummy, 0, None) == -1
+    assert lib.ifk_bwd_weight_reduce_many_f32(ctypes.byref(p), 0, None, 0, None, 0, None) == 0
+    assert lib.ifk_bwd_weight_reduce_many_f32(ctypes.byref(p), 3, dummy, 6, dummy, 0, None) == -2   # stride % 4
+    assert lib.ifk_bwd_weight_reduce_many_f32(ctypes.byref(p), 3, None, 8, dummy, 0, None) == -1
+    assert lib.ifk_bwd_weight_partial_f32(ctypes.byref(p), dummy, dummy, None, None) == -1
+    bad = _native.problem(2, 4, 5, 5, 3, 3, 4, 3)
+    assert lib.ifk_prepare_many_f32(ctypes.byref(bad), 1, dummy, 0, dummy, 0, None) == -3
+
+
+def test_describe_solve_variants(lib):
+    """resident kernel for model shapes, stream kernel (with and without a cluster) for images beyond
+    shared memory, plain fallback only where the reduction slice exceeds the register budget"""
+    d = lambda *a: _native.describe_solve(_native.problem(*a))
+    assert d(64, 12, 64, 64, 3, 3, 12, 1).startswith("stream<") and "cluster=1" in d(64, 12, 64, 64, 3, 3, 12, 1)
+    assert "cluster=4" in d(8, 96, 32, 32, 3, 3, 96, 1)
+    assert d(8, 48, 16, 16, 5, 5, 48, 1).startswith("global")
