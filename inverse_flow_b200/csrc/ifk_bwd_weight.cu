@@ -248,11 +248,44 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
     }
 }
 
+// one WARP per dW element: lanes stride over the chunks, then a fixed butterfly -- the summation
+// tree depends only on (nchunks), never on timing, so the result stays bit-reproducible
 __global__ void __launch_bounds__(256)
 bwd_weight_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int nchunks,
                          int C, int Cg, int Cw, int KH, int KW, size_t partial_stride, size_t dw_stride)
 {
     partial += (size_t)blockIdx.y * partial_stride;        // batched: blockIdx.y = layer
+    dw += (size_t)blockIdx.y * dw_stride;
+    const int K = KH * KW;
+    const int total = C * Cw * K;
+    const size_t chunk_stride = (size_t)C * Cg * K;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < total; e += warps_per_grid) {
+        const int a = e % K;
+        const int kc = (e / K) % Cw;
+        const int c = e / (K * Cw);
+        const int ah = a / KW, aw = a - ah * KW;
+        const int qh = KH - 1 - ah, qw = KW - 1 - aw;
+        const int cl = c % Cg;
+        float s = 0.f;
+        if (kc < Cg && !(qh == 0 && qw == 0 && kc >= cl)) {           // warp-uniform
+            const float *src = partial + ((size_t)c * Cg + kc) * K + (qh * KW + qw);
+            for (int n = lane; n < nchunks; n += 32) s += __ldg(src + (size_t)n * chunk_stride);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+            s = -s;
+        }
+        if (lane == 0) dw[e] = s;
+    }
+}
+
+// few chunks: one THREAD per dW element (a warp per element would leave most lanes idle)
+__global__ void __launch_bounds__(256)
+bwd_weight_reduce_thread_kernel(const float *__restrict__ partial, float *__restrict__ dw, int nchunks,
+                                int C, int Cg, int Cw, int KH, int KW, size_t partial_stride, size_t dw_stride)
+{
+    partial += (size_t)blockIdx.y * partial_stride;
     dw += (size_t)blockIdx.y * dw_stride;
     const int K = KH * KW;
     const int total = C * Cw * K;
@@ -267,16 +300,8 @@ bwd_weight_reduce_kernel(const float *__restrict__ partial, float *__restrict__ 
         float s = 0.f;
         if (kc < Cg && !(qh == 0 && qw == 0 && kc >= cl)) {
             const float *src = partial + ((size_t)c * Cg + kc) * K + (qh * KW + qw);
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // fixed association: still deterministic
-            int n = 0;
-            for (; n + 3 < nchunks; n += 4) {
-                s0 += __ldg(src + (size_t)n * chunk_stride);
-                s1 += __ldg(src + (size_t)(n + 1) * chunk_stride);
-                s2 += __ldg(src + (size_t)(n + 2) * chunk_stride);
-                s3 += __ldg(src + (size_t)(n + 3) * chunk_stride);
-            }
-            for (; n < nchunks; n++) s0 += __ldg(src + (size_t)n * chunk_stride);
-            s = -((s0 + s1) + (s2 + s3));
+            for (int n = 0; n < nchunks; n++) s += __ldg(src + (size_t)n * chunk_stride);
+            s = -s;
         }
         dw[e] = s;
     }
@@ -315,12 +340,22 @@ int launch_bwd_weight_reduce(const Geometry &g, int count, const void *workspace
     if (count <= 0) return 0;
     const BwdWeightPlan pl = make_plan(g);
     const int total = g.C * g.Cw * g.K;
-    int blocks = (total + 255) / 256;
-    if (blocks > kNumSM * 8) blocks = kNumSM * 8;
-    dim3 grid(blocks, count);
-    bwd_weight_reduce_kernel<<<grid, 256, 0, s>>>((const float *)workspace, dw, g.B > 0 ? pl.nchunks : 0, g.C,
-                                                  g.Cg, g.Cw, g.KH, g.KW, workspace_stride / sizeof(float),
-                                                  dw_stride);
+    const int nchunks = g.B > 0 ? pl.nchunks : 0;
+    const size_t pstride = workspace_stride / sizeof(float);
+    if (nchunks >= 16) {
+        int blocks = (total + 7) / 8;             // 8 warps per CTA, one element per warp
+        const int cap = kNumSM * 8 / (count < 8 ? count : 8) + 1;
+        if (blocks > cap) blocks = cap;
+        dim3 grid(blocks, count);
+        bwd_weight_reduce_kernel<<<grid, 256, 0, s>>>((const float *)workspace, dw, nchunks, g.C, g.Cg, g.Cw,
+                                                      g.KH, g.KW, pstride, dw_stride);
+    } else {
+        int blocks = (total + 255) / 256;
+        if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+        dim3 grid(blocks, count);
+        bwd_weight_reduce_thread_kernel<<<grid, 256, 0, s>>>((const float *)workspace, dw, nchunks, g.C, g.Cg,
+                                                             g.Cw, g.KH, g.KW, pstride, dw_stride);
+    }
     return cuda_status(cudaGetLastError());
 }
 
