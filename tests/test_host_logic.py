@@ -78,3 +78,21 @@ def test_if_glow_model_structure():
     c = glow.Coupling(8, 16)
     yc, ld = c(torch.randn(2, 8, 4, 4))
     assert ld.shape == (2,)
+
+
+def test_fincflow_layer_surface():
+    from inverse_flow_b200.layers import Finc_FlowUnit, PaddedConv2d
+    torch.manual_seed(0)
+    m = PaddedConv2d(4, 4, (3, 3), order='BR')
+    assert list(m.state_dict().keys()) == ["conv.weight"]
+    tl = m.tl_weight()
+    assert torch.all(torch.stack([tl[c, c, -1, -1] for c in range(4)]) == 1.0)      # unit diagonal
+    assert all(torch.all(tl[c, c + 1:, -1, -1] == 0) for c in range(4))              # masked upper triangle
+    assert torch.equal(torch.flip(m.conv.weight.data, [2, 3]), tl)                   # stored pre-flipped
+    out, ld = m(torch.randn(2, 4, 5, 6))                                             # forward is plain torch
+    assert out.shape == (2, 4, 5, 6) and ld == 0.0
+    unit = Finc_FlowUnit(8, 8, 3)
+    assert sorted(unit.state_dict().keys()) == ["conv_bl.conv.weight", "conv_br.conv.weight",
+                                                "conv_tl.conv.weight", "conv_tr.conv.weight"]
+    with pytest.raises(AssertionError):
+        Finc_FlowUnit(6, 6, 3)

@@ -404,3 +404,30 @@ def test_if_glow_model_trains_and_inverts():
     assert torch.isfinite(logp).all()
     rec = model.reverse([z.detach() for z in latents])
     np.testing.assert_allclose(rec.cpu().numpy(), x.cpu().numpy(), atol=1e-3)
+
+
+def test_fincflow_layers_reverse_through_the_inverse_kernels():
+    """PaddedConv2d.reverse (level 1, full C) and Finc_FlowUnit.reverse_level2
+    (one 4-group solve) invert the padded nn.Conv2d forward, for every corner order."""
+    from inverse_flow_b200.layers import Finc_FlowUnit, PaddedConv2d
+    torch.manual_seed(0)
+    for order in ("TL", "TR", "BL", "BR"):
+        m = PaddedConv2d(6, 6, (3, 3), order=order).cuda()
+        x = torch.randn(3, 6, 9, 7, device="cuda")
+        out, ld = m(x)
+        assert ld == 0.0 and out.shape == x.shape
+        rec, ld2 = m.reverse(out.detach())
+        np.testing.assert_allclose(rec.cpu().numpy(), x.cpu().numpy(), atol=1e-4)
+        # against the oracle in the layer's orientation
+        dims = {"TL": None, "TR": [3], "BL": [2], "BR": [2, 3]}[order]
+        flip = (lambda t: t) if dims is None else (lambda t: torch.flip(t, dims))
+        y_ref = oracle.inverse(flip(out.detach()).cpu().numpy().astype(np.float64),
+                               m.tl_weight().cpu().numpy().astype(np.float64), 1)
+        assert oracle.max_rel_err(flip(rec).cpu().numpy(), y_ref) < TOL
+    unit = Finc_FlowUnit(8, 8, (3, 3)).cuda()
+    x = torch.randn(2, 8, 6, 6, device="cuda")
+    out, _ = unit(x)
+    r2 = unit.reverse(out.detach())
+    r1 = unit.reverse_level1(out.detach())
+    np.testing.assert_allclose(r2.cpu().numpy(), x.cpu().numpy(), atol=1e-4)
+    np.testing.assert_allclose(r1.cpu().numpy(), r2.cpu().numpy(), atol=1e-5)
