@@ -195,10 +195,11 @@ static SolveConfig choose_config(const Geometry &g)
 
 bool solve_use_pdl()
 {
-    // programmatic dependent launch: measured slightly SLOWER on the chained model shapes
-    // (0.658 vs 0.610 ms per glow_mnist step), so it is opt-in
+    // programmatic dependent launch of the resident solve: the next solve's prologue (weights ->
+    // registers, zero fill) overlaps the current solve's wavefront: 0.430 -> 0.399 ms per glow_mnist
+    // step, 5.19 -> 4.80 ms per glow_imagenet32 step.  IFK_PDL=0 switches it off.
     const char *e = getenv("IFK_PDL");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 
 static long long *g_probe = nullptr;   // tuning aid, see ifk_debug_set_probe

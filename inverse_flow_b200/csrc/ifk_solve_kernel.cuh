@@ -226,8 +226,11 @@ solve_smem_kernel(const SolveParams p)
     float *out0 = p.out + (size_t)G * Cg * HW;
 
     // Programmatic dependent launch: let the next kernel of the stream start launching now, and do
-    // everything that touches no global memory (index tables, zero fill) before waiting for the
-    // previous kernel's results.  Both instructions are no-ops in a plain launch.
+    // everything that does not depend on the previous kernel's output before waiting for it: the
+    // shared-memory zero fill and -- the expensive part -- fetching this thread's weight slice and T.
+    // Reading the prepared weights ahead of the wait is safe because the only kernels that write
+    // them (prepare_kernel) never trigger programmatic completion: a solve launched behind a prepare
+    // does not start before the prepare has finished.  Both instructions are no-ops in a plain launch.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) smem[2] = 0.f;          // source of the opaque zero used by Hold (see above)
 
@@ -236,16 +239,7 @@ solve_smem_kernel(const SolveParams p)
     for (int i = tid * 4; i < p.YN; i += nthr * 4)
         *reinterpret_cast<float4 *>(ybuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-
     int b = blockIdx.x;
-    if (p.bulk && tid == 0) {
-        mbar_init(bar, 1);
-        if (b < p.B) {
-            mbar_expect_tx(bar, img_bytes);
-            bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
-        }
-    }
     const int NS = p.NS, NCT = p.NCT;
     const int ks = tid % NS;
     const int ct = (tid / NS) % NCT;
@@ -297,6 +291,14 @@ solve_smem_kernel(const SolveParams p)
             const int ci = i / p.CgP4, co = i - ci * p.CgP4;
             tT[i] = co < Cg ? __ldg(wg + (size_t)co * p.KDP + ci) : 0.f;
         }
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // the input image may only be touched from here on
+    if (p.bulk && tid == 0) {
+        mbar_init(bar, 1);
+        if (b < p.B) {
+            mbar_expect_tx(bar, img_bytes);
+            bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
+        }
+    }
     __syncthreads();        // T, mbarrier init, Hold's zero visible
     IFK_PROBE(1);
 
