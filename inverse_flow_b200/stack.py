@@ -83,38 +83,51 @@ class InvConvStack:
     def _stream(self):
         return _native.current_stream(self.device)
 
-    def forward(self):
+    def forward_stage(self, st):
         lib, s = self.lib, self._stream()
-        for st in self.stages:
-            p = ctypes.byref(st.problem)
-            _native.check(lib.ifk_prepare_many_f32(p, st.n, st.w_base.data_ptr(), st.w_stride,
-                                                   st.prepared_all.data_ptr(), st.pf, s))
-            for i in range(st.n):
-                _native.check(lib.ifk_inverse_f32(p, st.act[i].data_ptr(), st.prepared[i].data_ptr(),
-                                                  st.act[i + 1].data_ptr(), s))
+        p = ctypes.byref(st.problem)
+        _native.check(lib.ifk_prepare_many_f32(p, st.n, st.w_base.data_ptr(), st.w_stride,
+                                               st.prepared_all.data_ptr(), st.pf, s))
+        for i in range(st.n):
+            _native.check(lib.ifk_inverse_f32(p, st.act[i].data_ptr(), st.prepared[i].data_ptr(),
+                                              st.act[i + 1].data_ptr(), s))
 
-    def backward(self):
+    def backward_stage(self, st):
+        """dX chain on the current stream, dW stage 1 of every layer forked onto the side stream."""
         lib = self.lib
         main = torch.cuda.current_stream(self.device)
         s = ctypes.c_void_p(main.cuda_stream)
         side_s = ctypes.c_void_p(self.side.cuda_stream)
+        p = ctypes.byref(st.problem)
+        g = st.grad_in
+        for i in reversed(range(st.n)):
+            dx = st.dxs[i]
+            _native.check(lib.ifk_bwd_input_f32(p, g.data_ptr(), st.prepared[i].data_ptr(), dx.data_ptr(), s))
+            self.side.wait_stream(main)                       # fork: dW stage 1 needs this dX
+            ws = st.workspace[i * st.ws_floats:]
+            _native.check(lib.ifk_bwd_weight_partial_f32(p, dx.data_ptr(), st.act[i + 1].data_ptr(),
+                                                         ws.data_ptr(), side_s))
+            g = dx
+        st.dx = g
+
+    def finish_weight_gradients(self):
+        """join the side stream, then one batched dW stage 2 per stage into the flat bucket."""
+        main = torch.cuda.current_stream(self.device)
+        main.wait_stream(self.side)
+        s = ctypes.c_void_p(main.cuda_stream)
         for st in self.stages:
-            p = ctypes.byref(st.problem)
-            g = st.grad_in
-            for i in reversed(range(st.n)):
-                dx = st.dxs[i]
-                _native.check(lib.ifk_bwd_input_f32(p, g.data_ptr(), st.prepared[i].data_ptr(), dx.data_ptr(), s))
-                self.side.wait_stream(main)                       # fork: dW stage 1 needs this dX
-                ws = st.workspace[i * st.ws_floats:]
-                _native.check(lib.ifk_bwd_weight_partial_f32(p, dx.data_ptr(), st.act[i + 1].data_ptr(),
-                                                             ws.data_ptr(), side_s))
-                g = dx
-            st.dx = g
-        main.wait_stream(self.side)                               # join
-        for st in self.stages:
-            _native.check(lib.ifk_bwd_weight_reduce_many_f32(
+            _native.check(self.lib.ifk_bwd_weight_reduce_many_f32(
                 ctypes.byref(st.problem), st.n, st.workspace.data_ptr(), st.ws_floats * 4,
                 st.dw_base.data_ptr(), st.w_stride, s))
+
+    def forward(self):
+        for st in self.stages:
+            self.forward_stage(st)
+
+    def backward(self):
+        for st in self.stages:
+            self.backward_stage(st)
+        self.finish_weight_gradients()
 
     def forward_backward(self):
         self.forward()
@@ -153,22 +166,68 @@ class InvConvStack:
         hb["dw"] = torch.empty(self.grad_bucket.shape, **pin)
         return hb
 
+    def _host_pipeline(self, hb):
+        """x, g from pinned host memory -> forward + backward -> y, dX, dW to pinned host memory, with
+        the copies on their own stream: stage k+1's upload and stage k's download overlap compute."""
+        main = torch.cuda.current_stream(self.device)
+        cp = self.copy
+        cp.wait_stream(main)                                         # fork
+        ev_x, ev_g = [], []
+        with torch.cuda.stream(cp):
+            for st, x in zip(self.stages, hb["x"]):
+                st.act[0].copy_(x, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cp)
+                ev_x.append(ev)
+            for st, g in zip(self.stages, hb["g"]):
+                st.grad_in.copy_(g, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cp)
+                ev_g.append(ev)
+        for k, st in enumerate(self.stages):
+            main.wait_event(ev_x[k])
+            self.forward_stage(st)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(cp):
+                cp.wait_event(done)
+                hb["y"][k].copy_(st.act[st.n], non_blocking=True)
+        for k, st in enumerate(self.stages):
+            main.wait_event(ev_g[k])
+            self.backward_stage(st)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(cp):
+                cp.wait_event(done)
+                hb["dx"][k].copy_(st.dx, non_blocking=True)
+        self.finish_weight_gradients()
+        hb["dw"].copy_(self.grad_bucket, non_blocking=True)
+        main.wait_stream(cp)                                         # join
+
+    def capture_host(self, hb):
+        """the whole host-to-host step as ONE CUDA graph (memcpy nodes included)."""
+        with torch.cuda.device(self.device):
+            self.copy = torch.cuda.Stream(device=self.device)
+            warm = torch.cuda.Stream()
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                self._host_pipeline(hb)
+            torch.cuda.current_stream().wait_stream(warm)
+            torch.cuda.synchronize()
+            self.graph_host = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_host):
+                self._host_pipeline(hb)
+        self._host_buffers = hb
+        return self
+
     def step_host(self, hb):
         """host x, g -> device -> forward+backward -> host y, dX, dW.  Returns (h2d, d2h) bytes."""
-        h2d = d2h = 0
-        for st, x, g in zip(self.stages, hb["x"], hb["g"]):
-            st.act[0].copy_(x, non_blocking=True)
-            st.grad_in.copy_(g, non_blocking=True)
-            h2d += x.numel() * 4 + g.numel() * 4
-        self.step()
-        for st, y, dx in zip(self.stages, hb["y"], hb["dx"]):
-            y.copy_(st.act[st.n], non_blocking=True)
-            dx.copy_(st.dx, non_blocking=True)
-            d2h += y.numel() * 4 + dx.numel() * 4
-        hb["dw"].copy_(self.grad_bucket, non_blocking=True)
-        d2h += hb["dw"].numel() * 4
+        if getattr(self, "graph_host", None) is None or self._host_buffers is not hb:
+            self.capture_host(hb)
+        self.graph_host.replay()
         torch.cuda.current_stream(self.device).synchronize()
-        return h2d, d2h
+        n_act = sum(x.numel() for x in hb["x"])
+        return 2 * n_act * 4, 2 * n_act * 4 + hb["dw"].numel() * 4
 
     # -- accounting (BASELINE.md section 4) ----------------------------------------------
     def algorithmic_bytes_per_step(self):
