@@ -110,12 +110,12 @@ class InvConvStack:
             g = dx
         st.dx = g
 
-    def finish_weight_gradients(self):
+    def finish_weight_gradients(self, stages=None):
         """join the side stream, then one batched dW stage 2 per stage into the flat bucket."""
         main = torch.cuda.current_stream(self.device)
         main.wait_stream(self.side)
         s = ctypes.c_void_p(main.cuda_stream)
-        for st in self.stages:
+        for st in (self.stages if stages is None else stages):
             _native.check(self.lib.ifk_bwd_weight_reduce_many_f32(
                 ctypes.byref(st.problem), st.n, st.workspace.data_ptr(), st.ws_floats * 4,
                 st.dw_base.data_ptr(), st.w_stride, s))
@@ -145,6 +145,31 @@ class InvConvStack:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.forward_backward()
+        return self
+
+    def capture_bucketed(self):
+        """Two graphs for data-parallel runs, in the order a real model produces gradients: graph A =
+        forward of every stage + backward of the LAST stage (its slice of the bucket is then final),
+        graph B = backward of the remaining stages.  The caller all-reduces the last stage's bucket
+        slice asynchronously between the two replays, so that exchange overlaps graph B."""
+        with torch.cuda.device(self.device):
+            if self.graph is None:
+                self.capture()                    # warm-up and the single-graph variant
+            last, rest = self.stages[-1:], self.stages[:-1]
+            self.graph_a, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_a):
+                self.forward()
+                for st in last:
+                    self.backward_stage(st)
+                self.finish_weight_gradients(last)
+            with torch.cuda.graph(self.graph_b):
+                for st in rest:
+                    self.backward_stage(st)
+                self.finish_weight_gradients(rest)
+            n_last = sum(st.n * st.w_stride for st in last)
+            n_all = self.grad_bucket.numel()
+            self.bucket_last = self.grad_bucket[n_all - n_last:]
+            self.bucket_rest = self.grad_bucket[:n_all - n_last]
         return self
 
     def step(self):
