@@ -417,7 +417,7 @@ def run_ours(args):
     })
 
     # ---- CPU baseline + parity (rank 0, N == 1 only) ----------------------------------------
-    if world == 1:
+    if world == 1 and not args.no_cpu:
         threads = oracle.max_threads()
         per, reps_cpu, res = time_cpu(weights, xs, gs, groups_of, threads, budget_s=12.0)
         stack.step()
@@ -451,6 +451,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="glow_mnist", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true",
+                    help="skip the cpu_baseline / parity leg (for runs under a profiler; the line is then incomplete)")
     ap.add_argument("--groups", type=int, default=1,
                     help="channel groups; 1 = full coupling (the reference CPU solver), 0 = reference kernels' "
                          "rule (4 when C %% 4 == 0)")
