@@ -51,7 +51,7 @@ WORKLOADS = {
 # DRAM bytes (read + write) of ONE launch of the dominant kernel, from a committed ncu --set full
 # capture of that kernel at the workload's stage-1 shape: workload -> (bytes, where it is recorded)
 PROFILED_DRAM_TRAFFIC = {
-    "glow_mnist": (355328, "profiles/r01_ncu_solve_100x4x14.txt (dram__bytes_read 355328 + dram__bytes_write 0)"),
+    "glow_mnist": (355840, "profiles/r01_ncu_solve_100x4x14.txt (dram__bytes_read 355840 + dram__bytes_write 0)"),
 }
 
 CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
