@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define IFK_VERSION 100 /* major*10000 + minor*100 + patch */
+#define IFK_VERSION 200 /* major*10000 + minor*100 + patch */
 
 /* cudaStream_t without the CUDA headers (a driver-level CUstream handle). */
 typedef struct CUstream_st *ifk_stream_t;
@@ -51,7 +51,20 @@ enum ifk_status {
     IFK_ERR_BAD_SHAPE = -2,     /* a dimension is negative, or C/H/W/KH/KW is zero        */
     IFK_ERR_BAD_GROUPS = -3,    /* groups < 1, C % groups != 0 or Cw < C/groups          */
     IFK_ERR_UNSUPPORTED = -4,   /* shape exceeds what the kernels address */
-    IFK_ERR_NO_DEVICE = -5      /* no CUDA device / driver                               */
+    IFK_ERR_NO_DEVICE = -5,     /* no CUDA device / driver                               */
+    IFK_ERR_BAD_ORIENT = -6     /* orient is not one of IFK_ORIENT_*                     */
+};
+
+/* Corner the causal support grows from (the reference layers' `order`, inf/layers/inv_conv.py:
+ * 198-214: they flip the image -- and the stored weight -- around a top-left kernel).  Here the
+ * flips are index reflections inside the kernels, nothing is copied: with F the reflection of
+ * the listed axes, every operator below becomes F (.) F, e.g. ifk_inverse_f32 computes
+ * F L^-1 F x.  bit 0 = reflect W, bit 1 = reflect H. */
+enum ifk_orient {
+    IFK_ORIENT_TL = 0,  /* top-left (no reflection): inv_flow_no_pad and order 'TL' */
+    IFK_ORIENT_TR = 1,  /* reflect W */
+    IFK_ORIENT_BL = 2,  /* reflect H */
+    IFK_ORIENT_BR = 3   /* reflect both */
 };
 
 /* Geometry of one call.  B may be 0 (the call is a no-op that still validates). */
@@ -60,6 +73,7 @@ typedef struct ifk_problem {
     int KH, KW;     /* kernel taps                                              */
     int Cw;         /* second dimension of the weight tensor, >= C / groups     */
     int groups;     /* channel groups; the reference kernels hard-code 4        */
+    int orient;     /* IFK_ORIENT_*; 0 for the plain top-left operator          */
 } ifk_problem;
 
 int ifk_version(void);

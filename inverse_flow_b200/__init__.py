@@ -5,4 +5,4 @@ from . import functional
 from .functional import default_groups
 
 __all__ = ["functional", "default_groups"]
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -25,7 +25,7 @@ EXPORTS = (
 
 class Problem(ctypes.Structure):
     """struct ifk_problem"""
-    _fields_ = [(n, ctypes.c_int) for n in ("B", "C", "H", "W", "KH", "KW", "Cw", "groups")]
+    _fields_ = [(n, ctypes.c_int) for n in ("B", "C", "H", "W", "KH", "KW", "Cw", "groups", "orient")]
 
 
 class IfkError(RuntimeError):
@@ -78,8 +78,20 @@ def check(status):
         raise IfkError("ifk: CUDA error %d: %s" % (status, msg))
 
 
-def problem(B, C, H, W, KH, KW, Cw, groups):
-    return Problem(int(B), int(C), int(H), int(W), int(KH), int(KW), int(Cw), int(groups))
+ORIENTS = {"TL": 0, "TR": 1, "BL": 2, "BR": 3}      # enum ifk_orient: bit 0 reflects W, bit 1 reflects H
+
+
+def orient_code(orient):
+    """'TL' / 'TR' / 'BL' / 'BR' (the reference layers' `order`) or the IFK_ORIENT_* integer"""
+    if isinstance(orient, str):
+        if orient not in ORIENTS:
+            raise ValueError("unknown order: %r" % (orient,))
+        return ORIENTS[orient]
+    return int(orient)
+
+
+def problem(B, C, H, W, KH, KW, Cw, groups, orient=0):
+    return Problem(int(B), int(C), int(H), int(W), int(KH), int(KW), int(Cw), int(groups), orient_code(orient))
 
 
 def current_stream(device):

@@ -11,7 +11,8 @@ int make_geometry(const ifk_problem *p, Geometry *g)
         return IFK_ERR_BAD_SHAPE;
     if (p->groups < 1 || p->C % p->groups != 0 || p->Cw < p->C / p->groups) return IFK_ERR_BAD_GROUPS;
     g->B = p->B; g->C = p->C; g->H = p->H; g->W = p->W; g->KH = p->KH; g->KW = p->KW;
-    g->Cw = p->Cw; g->groups = p->groups;
+    if (p->orient < 0 || p->orient > 3) return IFK_ERR_BAD_ORIENT;
+    g->Cw = p->Cw; g->groups = p->groups; g->orient = p->orient;
     g->Cg = p->C / p->groups;
     g->K = p->KH * p->KW;
     // 32-bit index arithmetic inside one image / one weight tensor
@@ -44,6 +45,7 @@ const char *ifk_status_string(int status)
         case IFK_ERR_BAD_GROUPS: return "bad groups: need groups >= 1, C % groups == 0, Cw >= C/groups";
         case IFK_ERR_UNSUPPORTED: return "shape not supported by the kernels";
         case IFK_ERR_NO_DEVICE: return "no CUDA device";
+        case IFK_ERR_BAD_ORIENT: return "bad orient: need one of IFK_ORIENT_TL/TR/BL/BR (0..3)";
     }
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
     return "unknown ifk status";

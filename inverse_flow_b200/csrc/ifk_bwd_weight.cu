@@ -77,7 +77,7 @@ size_t bwd_weight_workspace_bytes(const Geometry &g)
 struct BwdWeightParams {
     const float *dx, *y;
     float *partial;
-    int B, C, H, W, KH, KW, Cg, ntk, items, per_chunk, nbuf, nstage, XN, bulk;
+    int B, C, H, W, KH, KW, Cg, ntk, items, per_chunk, nbuf, nstage, XN, bulk, orient;
 };
 
 // sum N per-lane values over the 32 lanes by recursive halving: N/2 + N/4 + ... shuffles
@@ -121,7 +121,11 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
     const int t = live ? item % K : 0, tile = live ? item / K : 0;
     const int c0 = (tile / p.ntk) * TC, k0 = (tile % p.ntk) * TK;
     const int qh = t / p.KW, qw = t - qh * p.KW;
-    const int aoff = c0 * HW, voff = k0 * HW - (qh * W + qw);
+    // orientation (ifk.h): on a reflected axis the neighbour p - q lies at a larger memory index
+    const bool fw = p.orient & 1, fh = p.orient & 2;
+    const int aoff = c0 * HW, voff = k0 * HW - ((fh ? -qh : qh) * W + (fw ? -qw : qw));
+    const int h_lo = fh ? 0 : qh, h_hi = fh ? p.H - 1 - qh : p.H - 1;     // rows / columns whose neighbour exists
+    const int w_lo = fw ? 0 : qw, w_hi = fw ? W - 1 - qw : W - 1;
     float acc[TC * TK];
 #pragma unroll
     for (int i = 0; i < TC * TK; i++) acc[i] = 0.f;
@@ -194,7 +198,7 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
             while (w >= W) { w -= W; h++; }
             while (h >= p.H) { h -= p.H; im++; }
             while (im < n_img) {
-                if (h >= qh && w >= qw) {
+                if (h >= h_lo && h <= h_hi && w >= w_lo && w <= w_hi) {
                     const int r = h * W + w;
                     float a[TC], v[TK];
                     if (staged) {
@@ -315,7 +319,7 @@ int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y
     p.dx = dx; p.y = y; p.partial = (float *)workspace;
     p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW; p.Cg = g.Cg;
     p.ntk = pl.ntk; p.items = pl.items; p.per_chunk = pl.per_chunk;
-    p.nbuf = pl.nbuf; p.nstage = pl.nstage; p.XN = pl.XN;
+    p.nbuf = pl.nbuf; p.nstage = pl.nstage; p.XN = pl.XN; p.orient = g.orient;
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) ? 1 : 0;
     if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;

@@ -17,7 +17,7 @@ namespace ifk {
 
 __global__ void __launch_bounds__(256)
 conv_tiled_kernel(const float *__restrict__ y, const float *__restrict__ weight, float *__restrict__ x,
-                  int B, int C, int H, int W, int KH, int KW, int Cw, int Cg, int CgP4, int nsplit)
+                  int B, int C, int H, int W, int KH, int KW, int Cw, int Cg, int CgP4, int nsplit, int orient)
 {
     extern __shared__ __align__(16) float wT[];              // [K][Cg][CgP4]
     const int HW = H * W, K = KH * KW;
@@ -39,6 +39,8 @@ conv_tiled_kernel(const float *__restrict__ y, const float *__restrict__ weight,
     __syncthreads();
 
     const int nquad = CgP4 >> 2;
+    const bool fw = orient & 1, fh = orient & 2;              // reflected axes (ifk.h IFK_ORIENT_*)
+    const int step_h = fh ? -W : W, step_w = fw ? -1 : 1;     // memory step towards the neighbour's side
     // work unit = (image, split): the items of one image may be shared by `nsplit` CTAs
     for (int u = blockIdx.x; u < B * nsplit; u += gridDim.x) {
         const int b = u / nsplit, sp = u - b * nsplit;
@@ -46,12 +48,13 @@ conv_tiled_kernel(const float *__restrict__ y, const float *__restrict__ weight,
         float *xb = x + ((size_t)b * C + (size_t)G * Cg) * HW;
         for (int item = sp * blockDim.x + tid; item < HW * nquad; item += nsplit * blockDim.x) {
             const int cq = item / HW, r = item - cq * HW;
-            const int h = r / W, w = r - h * W;
+            const int hm = r / W, wm = r - hm * W;
+            const int h = fh ? H - 1 - hm : hm, w = fw ? W - 1 - wm : wm;     // causal-frame coordinates
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             const int qh_max = h < KH - 1 ? h : KH - 1, qw_max = w < KW - 1 ? w : KW - 1;
             for (int qh = 0; qh <= qh_max; qh++)
                 for (int qw = 0; qw <= qw_max; qw++) {
-                    const float *yp = yb + r - qh * W - qw;
+                    const float *yp = yb + r - qh * step_h - qw * step_w;
                     const float *wp = wT + (size_t)(qh * KW + qw) * Cg * CgP4 + cq * 4;
 #pragma unroll 4
                     for (int ci = 0; ci < Cg; ci++) {
@@ -74,9 +77,11 @@ conv_tiled_kernel(const float *__restrict__ y, const float *__restrict__ weight,
 
 __global__ void __launch_bounds__(256)
 conv_kernel(const float *__restrict__ y, const float *__restrict__ weight, float *__restrict__ x,
-            int B, int C, int H, int W, int KH, int KW, int Cw, int Cg)
+            int B, int C, int H, int W, int KH, int KW, int Cw, int Cg, int orient)
 {
     const int HW = H * W;
+    const bool fw = orient & 1, fh = orient & 2;
+    const int step_h = fh ? -W : W, step_w = fw ? -1 : 1;
     const size_t total = (size_t)B * C * HW;
     const size_t tap_stride = (size_t)KH * KW, row_stride = (size_t)Cw * tap_stride;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -84,7 +89,8 @@ conv_kernel(const float *__restrict__ y, const float *__restrict__ weight, float
         const int r = (int)(e % HW);
         const int c = (int)((e / HW) % C);
         const size_t b = e / ((size_t)HW * C);
-        const int h = r / W, w = r - h * W;
+        const int hm = r / W, wm = r - hm * W;
+        const int h = fh ? H - 1 - hm : hm, w = fw ? W - 1 - wm : wm;
         const int base = (c / Cg) * Cg, cl = c - base;
         const float *yb = y + (b * C + base) * HW;
         const float *wr = weight + (size_t)c * row_stride;
@@ -93,7 +99,7 @@ conv_kernel(const float *__restrict__ y, const float *__restrict__ weight, float
         for (int qh = 0; qh <= qh_max; qh++)
             for (int qw = 0; qw <= qw_max; qw++) {
                 const int a = (KH - 1 - qh) * KW + (KW - 1 - qw);
-                const int rn = r - qh * W - qw;
+                const int rn = r - qh * step_h - qw * step_w;
                 const int kc_end = (qh == 0 && qw == 0) ? cl : Cg;   // strictly lower centre tap
                 for (int kc = 0; kc < kc_end; kc++)
                     acc = fmaf(__ldg(wr + kc * tap_stride + a), __ldg(yb + kc * HW + rn), acc);
@@ -126,13 +132,13 @@ int launch_conv(const Geometry &g, const float *y, const float *weight, float *x
         if (grid_x > g.B * nsplit) grid_x = g.B * nsplit;
         dim3 grid(grid_x, g.groups);
         conv_tiled_kernel<<<grid, 256, smem, s>>>(y, weight, x, g.B, g.C, g.H, g.W, g.KH, g.KW, g.Cw, g.Cg, CgP4,
-                                                  nsplit);
+                                                  nsplit, g.orient);
         return cuda_status(cudaGetLastError());
     }
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)kNumSM * 32;
     if (blocks > cap) blocks = cap;
-    conv_kernel<<<(unsigned)blocks, 256, 0, s>>>(y, weight, x, g.B, g.C, g.H, g.W, g.KH, g.KW, g.Cw, g.Cg);
+    conv_kernel<<<(unsigned)blocks, 256, 0, s>>>(y, weight, x, g.B, g.C, g.H, g.W, g.KH, g.KW, g.Cw, g.Cg, g.orient);
     return cuda_status(cudaGetLastError());
 }
 

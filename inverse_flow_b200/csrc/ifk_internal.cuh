@@ -11,6 +11,7 @@ constexpr int kMaxSmemBytes = 227 * 1024; // opt-in dynamic shared memory per CT
 
 struct Geometry {
     int B, C, H, W, KH, KW, Cw, groups;
+    int orient;  // IFK_ORIENT_*: bit 0 reflects W, bit 1 reflects H
     int Cg;   // channels per group
     int K;    // KH * KW taps (tap 0 = the centre / "x" tap)
     int KD;   // K * Cg : length of one prepared weight row

@@ -36,6 +36,8 @@ solve_global_kernel(const SolveParams p)
     const int G = blockIdx.y;
     const float *wg = p.prep + (size_t)G * Cg * p.KDP;
     const int ndiag = H + W - 1;
+    const int sw = (p.flip & 1) ? -1 : 1, sh = (p.flip & 2) ? -1 : 1;
+    const int idx0 = ((p.flip & 2) ? (H - 1) * W : 0) + ((p.flip & 1) ? W - 1 : 0);
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         const size_t gbase = ((size_t)b * p.C + (size_t)G * Cg) * HW;
         const float *in = p.in + gbase;
@@ -47,15 +49,13 @@ solve_global_kernel(const SolveParams p)
             for (int e = threadIdx.x; e < work; e += blockDim.x) {
                 const int co = e % Cg, h = hmin + e / Cg, w = d - h;
                 const float *wr = wg + (size_t)co * p.KDP;
-                const int r = h * W + w;
-                const int gr = p.reverse ? HW - 1 - r : r;
+                const int gr = idx0 + sh * h * W + sw * w;        // memory index of solver pixel (h, w)
                 float acc = 0.f;
                 for (int ci = 0; ci < Cg; ci++) acc = fmaf(__ldg(wr + ci), in[ci * HW + gr], acc);
                 for (int t = 1; t < K; t++) {
                     const int qh = t / KW, qw = t - qh * KW;
                     if (h - qh < 0 || w - qw < 0) continue;
-                    const int rn = (h - qh) * W + (w - qw);
-                    const int gn = p.reverse ? HW - 1 - rn : rn;
+                    const int gn = gr - sh * qh * W - sw * qw;
                     const float *wt = wr + t * Cg;
                     for (int ci = 0; ci < Cg; ci++)
                         acc = fmaf(__ldg(wt + ci), __ldcg(out + ci * HW + gn), acc);
@@ -214,7 +214,7 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
     p.in = in; p.out = out; p.prep = prep_dir;
     p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW;
     p.Cg = g.Cg; p.KD = g.KD; p.KDP = g.KDP;
-    p.reverse = reverse ? 1 : 0;
+    p.flip = reverse ? (g.orient ^ 3) : g.orient;     // the adjoint walks the fully reflected frame
     p.probe = g_probe;
     dim3 grid(c.grid_x, g.groups);
     if (!c.smem) {

@@ -18,8 +18,8 @@
 //      combined by full-warp shuffles, the ks == 0 lane adds z and writes y into `ybuf`
 //      (for later diagonals) and in place into `zbuf`; one block barrier per diagonal;
 //   4. `zbuf` returns to global memory by one TMA bulk store.
-// The adjoint solve (reverse) is the same walk in reflected coordinates: only the index into
-// the contiguous buffers is mirrored.
+// The adjoint solve is the same walk in reflected coordinates, and so are the TR/BL/BR
+// orientations (ifk.h): only the index into the contiguous buffers is mirrored (`flip`).
 #pragma once
 #include "ifk_internal.cuh"
 
@@ -41,7 +41,8 @@ struct SolveParams {
     int v_dt, v_dq;     // NS / CgV and NS % CgV: how a thread's vector index advances per j
     int NS, NCT, nslots, iters;
     int nwork;          // threads that walk the wavefront (multiple of 32); the rest only help staging
-    int reverse;
+    int flip;           // memory index of solver pixel (h, w): bit 0 -> column W-1-w, bit 1 -> row H-1-h
+                        // (adjoint solve = both reflected; IFK_ORIENT_* reflections are XORed in)
     int bulk;           // image size / pointers allow TMA bulk copies (16-byte granularity)
     int walign;         // prepared weights are 16-byte aligned (128-bit weight loads allowed)
     long long *probe;   // tuning aid: clock64() stamps of CTA (0,0) thread 0, or nullptr
@@ -326,10 +327,12 @@ solve_smem_kernel(const SolveParams p)
     const uint32_t pix_step = hold((uint32_t)PS * 4u);                                   // per diagonal
     const uint32_t pix_row = hold((uint32_t)(nslots * (WP - 1) * PS) * 4u);              // per row iteration
     const uint32_t pix0 = ybase + (uint32_t)(slot * (WP - 1) * PS) * 4u;                 // d = 0, it = 0
-    const uint32_t z_step = hold(p.reverse ? (uint32_t)(-4) : 4u);
-    const uint32_t z_row = hold((uint32_t)(nslots * (W - 1)) * z_step);
-    const uint32_t z0 = smem_u32(zbuf) + (uint32_t)(own_c0 * HW) * 4u +
-                        (p.reverse ? (uint32_t)(HW - 1 - slot * (W - 1)) * 4u : (uint32_t)(slot * (W - 1)) * 4u);
+    // contiguous index of solver pixel (h, w) = idx0 + sh*h*W + sw*w  (sh, sw = -1 on a reflected axis)
+    const int sw = (p.flip & 1) ? -1 : 1, sh = (p.flip & 2) ? -1 : 1;
+    const int idx0 = ((p.flip & 2) ? (H - 1) * W : 0) + ((p.flip & 1) ? W - 1 : 0);
+    const uint32_t z_step = hold((uint32_t)(sw * 4));
+    const uint32_t z_row = hold((uint32_t)(nslots * (sh * W - sw) * 4));
+    const uint32_t z0 = smem_u32(zbuf) + (uint32_t)(own_c0 * HW) * 4u + (uint32_t)((idx0 + slot * (sh * W - sw)) * 4);
     const uint32_t own_c0_bytes = hold((uint32_t)own_c0 * 4u);
     const int slot_r = hold(slot);
     uint32_t parity = 0;

@@ -31,7 +31,7 @@ struct StreamParams {
     int NVT;            // (K-1)*Cg reduction entries per output
     int NS, NCT, nslots, iters, nwork;
     int kw_magic, v_dt, v_dq;
-    int reverse;
+    int flip;           // as SolveParams::flip
     int csize;          // CTAs per cluster (1 = no cluster); CTA r owns channel tiles [r*NCT, (r+1)*NCT)
 };
 
@@ -105,14 +105,14 @@ solve_stream_kernel(const StreamParams p)
     float wreg[CC][NV];
     int offs[NV], qhw[NV];
     {
-        const int sgn = p.reverse ? 1 : -1;                 // reflected walk: neighbours lie ahead in memory
+        const int sw = (p.flip & 1) ? -1 : 1, sh = (p.flip & 2) ? -1 : 1;   // reflected axis: neighbours lie ahead in memory
         int t1 = ks / Cg, q = ks - t1 * Cg;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const bool valid = worker && j * NS + ks < p.NVT;
             const int t = t1 + 1;
             const int qh = (t * p.kw_magic) >> 16, qw = t - qh * p.KW;
-            offs[j] = valid ? q * HW + sgn * (qh * W + qw) : 0;
+            offs[j] = valid ? q * HW - (sh * qh * W + sw * qw) : 0;
             qhw[j] = valid ? ((qh << 8) | qw) : 0x7f7f;      // padding entries never pass the border test
 #pragma unroll
             for (int cc = 0; cc < CC; cc++) {
@@ -139,6 +139,8 @@ solve_stream_kernel(const StreamParams p)
     const int own_c0 = ct * CC + own_off;
     const int ndiag = H + W - 1;
     const int KH1 = p.KH - 1, KW1 = p.KW - 1;
+    const int sw_1 = (p.flip & 1) ? -1 : 1, sh_w = (p.flip & 2) ? -W : W;
+    const int idx0 = ((p.flip & 2) ? (H - 1) * W : 0) + ((p.flip & 1) ? W - 1 : 0);
 
     const int nclusters = CL ? gridDim.x / p.csize : gridDim.x;
     for (int b = CL ? blockIdx.x / p.csize : blockIdx.x; b < p.B; b += nclusters) {
@@ -177,8 +179,7 @@ solve_stream_kernel(const StreamParams p)
                     const int w = d - h;
                     const bool active = worker && h < H && (unsigned)w < (unsigned)W;
                     if (!__any_sync(0xffffffffu, active)) continue;        // warp-uniform
-                    const int rr = active ? h * W + w : 0;
-                    const int m = p.reverse ? HW - 1 - rr : rr;
+                    const int m = active ? idx0 + sh_w * h + sw_1 * w : 0;   // memory index of solver pixel (h, w)
                     float *base = out_b + m;
                     const int hh = active ? h : -1, ww = active ? w : -1;  // idle lanes load nothing
 
@@ -315,7 +316,7 @@ int launch_solve_stream(const Geometry &g, const float *in, const float *prep_di
     p.NS = c.ns; p.NCT = c.nct; p.nslots = c.nslots; p.iters = c.iters; p.nwork = c.nwork;
     p.kw_magic = (65536 + g.KW - 1) / g.KW;
     p.v_dt = c.ns / g.Cg; p.v_dq = c.ns % g.Cg;
-    p.reverse = reverse ? 1 : 0;
+    p.flip = reverse ? (g.orient ^ 3) : g.orient;
     p.csize = c.csize;
     dim3 grid(c.grid_x, g.groups);
     cudaLaunchConfig_t cfg{};

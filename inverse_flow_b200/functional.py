@@ -31,7 +31,7 @@ def _check_activation(t, name):
         raise RuntimeError("%s must be contiguous" % name)
 
 
-def _problem(x, weight, groups):
+def _problem(x, weight, groups, orient=0):
     _check_activation(x, "input")
     _check_activation(weight, "kernel")
     if weight.device != x.device:
@@ -43,7 +43,7 @@ def _problem(x, weight, groups):
         groups = default_groups(C)
     if min(C, H, W, weight.shape[1], weight.shape[2], weight.shape[3]) == 0:
         raise ValueError("zero-sized channel / spatial / kernel dimension")
-    return _native.problem(B, C, H, W, weight.shape[2], weight.shape[3], weight.shape[1], groups)
+    return _native.problem(B, C, H, W, weight.shape[2], weight.shape[3], weight.shape[1], groups, orient)
 
 
 def _ptr(t):
@@ -70,7 +70,7 @@ class Prepared:
             _native.check(lib.ifk_prepare_f32(ctypes.byref(p), _ptr(weight), _ptr(self.buffer),
                                               _native.current_stream(weight.device)))
 
-    def for_batch(self, x):
+    def for_batch(self, x, orient=0):
         C, Cw, KH, KW = self.weight_shape
         if x.shape[1] != C:
             raise ValueError("kernel has %d output rows, input has %d channels" % (C, x.shape[1]))
@@ -78,20 +78,22 @@ class Prepared:
             raise RuntimeError("input and kernel live on different devices")
         if x.shape[2] == 0 or x.shape[3] == 0:
             raise ValueError("zero-sized spatial dimension")
-        return _native.problem(x.shape[0], C, x.shape[2], x.shape[3], KH, KW, Cw, self.groups)
+        return _native.problem(x.shape[0], C, x.shape[2], x.shape[3], KH, KW, Cw, self.groups, orient)
 
 
 def prepare(weight, groups=None):
     return Prepared(weight, groups)
 
 
-def inverse(x, weight, groups=None, out=None, prepared=None):
-    """y = L^-1 x (training direction).  `out` may be supplied (reference call style)."""
+def inverse(x, weight, groups=None, out=None, prepared=None, orient=0):
+    """y = L^-1 x (training direction).  `out` may be supplied (reference call style).
+    `orient` ('TL'/'TR'/'BL'/'BR' or IFK_ORIENT_*): the corner the causal support grows from; every
+    function of this module then computes F (.) F with F the reflection, inside the kernel."""
     lib = _native.load()
     if prepared is None:
         prepared = Prepared(weight, groups)
     _check_activation(x, "input")
-    p = prepared.for_batch(x)
+    p = prepared.for_batch(x, orient)
     if out is None:
         out = torch.empty_like(x)
     else:
@@ -106,10 +108,10 @@ def inverse(x, weight, groups=None, out=None, prepared=None):
     return out
 
 
-def conv(y, weight, groups=None, out=None):
+def conv(y, weight, groups=None, out=None, orient=0):
     """x = L y (sampling direction); takes the raw weight."""
     lib = _native.load()
-    p = _problem(y, weight, groups)
+    p = _problem(y, weight, groups, orient)
     if out is None:
         out = torch.empty_like(y)
     else:
@@ -124,13 +126,13 @@ def conv(y, weight, groups=None, out=None):
     return out
 
 
-def bwd_input(grad, weight, groups=None, out=None, prepared=None):
+def bwd_input(grad, weight, groups=None, out=None, prepared=None, orient=0):
     """dX = L^-T grad."""
     lib = _native.load()
     if prepared is None:
         prepared = Prepared(weight, groups)
     _check_activation(grad, "grad_output")
-    p = prepared.for_batch(grad)
+    p = prepared.for_batch(grad, orient)
     if out is None:
         out = torch.empty_like(grad)
     with torch.cuda.device(grad.device):
@@ -139,10 +141,10 @@ def bwd_input(grad, weight, groups=None, out=None, prepared=None):
     return out
 
 
-def bwd_weight(dx, y, weight, groups=None, out=None):
+def bwd_weight(dx, y, weight, groups=None, out=None, orient=0):
     """dW = -corr(dX, y), shaped like `weight`."""
     lib = _native.load()
-    p = _problem(dx, weight, groups)
+    p = _problem(dx, weight, groups, orient)
     _check_activation(y, "saved output")
     if y.shape != dx.shape:
         raise ValueError("dx and y shapes differ")
@@ -156,7 +158,7 @@ def bwd_weight(dx, y, weight, groups=None, out=None):
     return out
 
 
-def backward(grad, y, weight, groups=None, prepared=None):
+def backward(grad, y, weight, groups=None, prepared=None, orient=0):
     """(dX, dW) for upstream `grad` at the saved output `y` -- one C call."""
     lib = _native.load()
     if prepared is None:
@@ -165,7 +167,7 @@ def backward(grad, y, weight, groups=None, prepared=None):
     _check_activation(y, "saved output")
     if y.shape != grad.shape:
         raise ValueError("grad_output and saved output shapes differ")
-    p = prepared.for_batch(grad)
+    p = prepared.for_batch(grad, orient)
     dx = torch.empty_like(grad)
     dw = torch.empty_like(weight)
     nbytes = lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(p))

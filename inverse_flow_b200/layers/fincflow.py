@@ -73,8 +73,8 @@ class PaddedConv2d(FlowLayer):
         """-> (y, 0.0) like the reference's reverse_cython / reverse_cuda (conv.py:166, 219)."""
         if self.conv.bias is not None:
             x = x - self.conv.bias.reshape(1, -1, 1, 1)
-        y = IF.inverse(_flip(x, self.order).contiguous(), self.tl_weight(), groups=1)
-        return _flip(y, self.order), 0.0
+        # the image is not flipped: the kernel walks it from the layer's corner (ifk.h IFK_ORIENT_*)
+        return IF.inverse(x.contiguous(), self.tl_weight(), groups=1, orient=self.order), 0.0
 
     def logdet(self, x, context=None):
         return 0.0

@@ -11,8 +11,10 @@ Deliberate differences, all documented in DESIGN.md:
   * backward returns the true gradients (dX = L^-T g, dW = -corr(dX, y)), SURVEY.md 0.4;
   * the saved tensors are (y, W), not (x, W, y); no CPU-side scratch allocations
     (reference inv_conv.py:70-77 builds a (B,C,k,k,H,W) tensor on the host every call);
-  * orders TR/BL/BR flip the *data* and leave `weight_fwd` untouched, and `reverse` applies
-    the same flips, so every order round-trips (the reference re-flips the stored weight on
+  * orders TR/BL/BR act as F L^-1 F with F the reflection of the order's axes -- what flipping
+    the data around a top-left kernel computes -- but as index reflections inside the kernels
+    (`orient`, ifk.h), without flip copies; `weight_fwd` is left untouched and `reverse` uses the
+    same orientation, so every order round-trips (the reference re-flips the stored weight on
     every call and never flips in reverse, inv_conv.py:198-214, 249-267);
   * `groups`: None -> the reference's 4 channel groups when C % 4 == 0, else 1.
 """
@@ -25,31 +27,29 @@ from torch.nn.modules.utils import _pair
 from .. import functional as IF
 from .flowlayer import FlowLayer, mark_expensive
 
-_FLIP_DIMS = {"TL": None, "TR": [3], "BL": [2], "BR": [2, 3]}
-
-
 class inv_conv_(autograd.Function):
     """y = L^-1 x with its parallel backward (reference inv_conv.py:43-86)."""
 
     @staticmethod
-    def forward(ctx, x, W, groups=None):
+    def forward(ctx, x, W, groups=None, orient=0):
         x = x.contiguous()
         Wc = W.contiguous()
         prepared = IF.Prepared(Wc, groups)
-        y = IF.inverse(x, Wc, prepared=prepared)
+        y = IF.inverse(x, Wc, prepared=prepared, orient=orient)
         ctx.save_for_backward(y, Wc)
         ctx.prepared = prepared
+        ctx.orient = orient
         return y
 
     @staticmethod
     def backward(ctx, output_grad):
         y, W = ctx.saved_tensors
-        dx, dw = IF.backward(output_grad.contiguous(), y, W, prepared=ctx.prepared)
-        return dx, dw, None
+        dx, dw = IF.backward(output_grad.contiguous(), y, W, prepared=ctx.prepared, orient=ctx.orient)
+        return dx, dw, None, None
 
 
-def inv_conv_4d(x, W, groups=None):
-    return inv_conv_.apply(x, W, groups)
+def inv_conv_4d(x, W, groups=None, orient=0):
+    return inv_conv_.apply(x, W, groups, orient)
 
 
 class _InvFlowBase(FlowLayer):
@@ -101,20 +101,16 @@ class _InvFlowBase(FlowLayer):
             self.mask = self.get_mask()
             self.weight_fwd.grad = self.weight_fwd.grad * self.mask.to(self.weight_fwd.grad.device)
 
-    def _flip(self, t):
-        dims = _FLIP_DIMS[getattr(self, "order", "TL")]
-        return t if dims is None else torch.flip(t, dims)
-
     def forward(self, input, context=None, compute_expensive=False):
         if self.training:
             self.logabsdet_dirty = True
         self.input = input
-        self.output = self._flip(inv_conv_4d(self._flip(input), self.weight_fwd, self.groups))
+        self.output = inv_conv_4d(input, self.weight_fwd, self.groups, getattr(self, "order", "TL"))
         return self.output, 0.0
 
     def reverse(self, input, context=None, compute_expensive=False):
-        x = IF.conv(self._flip(input).contiguous(), self.weight_fwd.detach().contiguous(), groups=self.groups)
-        return self._flip(x)
+        return IF.conv(input.contiguous(), self.weight_fwd.detach().contiguous(), groups=self.groups,
+                       orient=getattr(self, "order", "TL"))
 
     @mark_expensive
     def logdet(self, input, context=None, compute_expensive=False):

@@ -83,28 +83,38 @@ def _call(name, first, w, groups, threads, second=None, out_like=None):
     return out
 
 
-def inverse(x, w, groups=1, threads=1, wavefront=False):
-    """y = L^-1 x  (solve_mc.py:88-114; wavefront=True follows solve_mc.py:8-50)."""
-    x = _prep(x, x.dtype)
-    return _call("inverse_wavefront" if wavefront else "inverse", x, w, groups, threads)
+_ORIENT_AXES = {0: (), 1: (3,), 2: (2,), 3: (2, 3), "TL": (), "TR": (3,), "BL": (2,), "BR": (2, 3)}
 
 
-def conv(y, w, groups=1, threads=1):
-    """x = L y, the masked convolution (sampling direction)."""
-    y = _prep(y, y.dtype)
-    return _call("conv", y, w, groups, threads)
+def _reflect(a, orient):
+    """F a: the image reflected along the axes of an orientation (a copy; the reference layers do
+    exactly this with torch.flip around their top-left kernels, inf/layers/inv_conv.py:198-214)."""
+    axes = _ORIENT_AXES[orient]
+    return np.ascontiguousarray(np.flip(a, axes)) if axes else a
 
 
-def bwd_input(g, w, groups=1, threads=1):
-    """dX = L^-T g."""
-    g = _prep(g, g.dtype)
-    return _call("bwd_input", g, w, groups, threads)
+def inverse(x, w, groups=1, threads=1, wavefront=False, orient=0):
+    """y = F L^-1 F x  (solve_mc.py:88-114; wavefront=True follows solve_mc.py:8-50)."""
+    x = _prep(_reflect(x, orient), x.dtype)
+    return _reflect(_call("inverse_wavefront" if wavefront else "inverse", x, w, groups, threads), orient)
 
 
-def bwd_weight(dx, y, w_shape, groups=1, threads=1):
-    """dW = -corr(dX, y), shaped like the weight (C, Cw, KH, KW)."""
-    dx = _prep(dx, dx.dtype)
-    y = _prep(y, dx.dtype)
+def conv(y, w, groups=1, threads=1, orient=0):
+    """x = F L F y, the masked convolution (sampling direction)."""
+    y = _prep(_reflect(y, orient), y.dtype)
+    return _reflect(_call("conv", y, w, groups, threads), orient)
+
+
+def bwd_input(g, w, groups=1, threads=1, orient=0):
+    """dX = F L^-T F g."""
+    g = _prep(_reflect(g, orient), g.dtype)
+    return _reflect(_call("bwd_input", g, w, groups, threads), orient)
+
+
+def bwd_weight(dx, y, w_shape, groups=1, threads=1, orient=0):
+    """dW = -corr(F dX, F y), shaped like the weight (C, Cw, KH, KW)."""
+    dx = _prep(_reflect(dx, orient), dx.dtype)
+    y = _prep(_reflect(y, orient), dx.dtype)
     w_like = np.empty(w_shape, dtype=dx.dtype)
     fn = getattr(lib(), "ifk_oracle_bwd_weight_%s" % _suffix(dx.dtype))
     fn.restype = None
@@ -113,10 +123,10 @@ def bwd_weight(dx, y, w_shape, groups=1, threads=1):
     return w_like
 
 
-def backward(g, y, w, groups=1, threads=1):
+def backward(g, y, w, groups=1, threads=1, orient=0):
     """(dX, dW) for upstream gradient g at saved output y."""
-    dx = bwd_input(g, w, groups, threads)
-    return dx, bwd_weight(dx, y, w.shape, groups, threads)
+    dx = bwd_input(g, w, groups, threads, orient)
+    return dx, bwd_weight(dx, y, w.shape, groups, threads, orient)
 
 
 def literal_inverse(x, w):

@@ -31,9 +31,9 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_version_and_status_strings(lib):
-    assert lib.ifk_version() == 100
+    assert lib.ifk_version() == 200
     assert lib.ifk_status_string(0) == b"ok"
-    for code in (-1, -2, -3, -4, -5):
+    for code in (-1, -2, -3, -4, -5, -6):
         assert lib.ifk_status_string(code) not in (b"ok", b"unknown ifk status")
 
 
@@ -50,6 +50,7 @@ def test_sizes(lib):
 @pytest.mark.parametrize("kwargs,code", [
     (dict(C=0), -2), (dict(H=0), -2), (dict(KH=0), -2), (dict(B=-1), -2),
     (dict(groups=0), -3), (dict(groups=5), -3), (dict(groups=4, Cw=2), -3),
+    (dict(orient=4), -6), (dict(orient=-1), -6),
 ])
 def test_bad_geometry_is_rejected_before_any_launch(lib, kwargs, code):
     base = dict(B=2, C=12, H=8, W=8, KH=3, KW=3, Cw=12, groups=1)
@@ -61,6 +62,15 @@ def test_bad_geometry_is_rejected_before_any_launch(lib, kwargs, code):
     assert lib.ifk_prepared_floats(ctypes.byref(p)) == 0
     with pytest.raises(ValueError):
         _native.check(code)
+
+
+def test_problem_struct_matches_the_header():
+    """ifk_problem is nine ints, `orient` last (include/ifk.h); names map to IFK_ORIENT_*"""
+    assert ctypes.sizeof(_native.Problem) == 9 * ctypes.sizeof(ctypes.c_int)
+    assert [f[0] for f in _native.Problem._fields_][-1] == "orient"
+    assert [_native.problem(1, 4, 5, 5, 3, 3, 4, 1, o).orient for o in ("TL", "TR", "BL", "BR")] == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        _native.problem(1, 4, 5, 5, 3, 3, 4, 1, "XX")
 
 
 def test_null_pointers_are_rejected(lib):

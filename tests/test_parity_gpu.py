@@ -30,21 +30,22 @@ def dev(a):
     return torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
 
 
-def run_all(IF, x, w, g, groups):
+def run_all(IF, x, w, g, groups, orient=0):
     """inverse, conv, dX, dW on the GPU; float64 oracle beside it.  Returns error dict."""
     xd, wd, gd = dev(x), dev(w), dev(g)
-    y = IF.inverse(xd, wd, groups=groups)
-    rec = IF.conv(y, wd, groups=groups)
-    dx, dw = IF.backward(gd, y, wd, groups=groups)
+    y = IF.inverse(xd, wd, groups=groups, orient=orient)
+    rec = IF.conv(y, wd, groups=groups, orient=orient)
+    dx, dw = IF.backward(gd, y, wd, groups=groups, orient=orient)
     torch.cuda.synchronize()
     x64, w64, g64 = (np.asarray(a, dtype=np.float64) for a in (x.astype(np.float32), w.astype(np.float32),
                                                                 g.astype(np.float32)))
-    y_ref = oracle.inverse(x64, w64, groups, threads=4)
-    dx_ref, dw_ref = oracle.backward(g64, y_ref, w64, groups, threads=4)
+    y_ref = oracle.inverse(x64, w64, groups, threads=4, orient=orient)
+    dx_ref, dw_ref = oracle.backward(g64, y_ref, w64, groups, threads=4, orient=orient)
     return {
         "y": oracle.max_rel_err(y.cpu().numpy(), y_ref),
         "rec": oracle.max_rel_err(rec.cpu().numpy(), x64),
-        "conv": oracle.max_rel_err(rec.cpu().numpy(), oracle.conv(y.cpu().numpy().astype(np.float64), w64, groups)),
+        "conv": oracle.max_rel_err(rec.cpu().numpy(),
+                                   oracle.conv(y.cpu().numpy().astype(np.float64), w64, groups, orient=orient)),
         "dx": oracle.max_rel_err(dx.cpu().numpy(), dx_ref),
         "dw": oracle.max_rel_err(dw.cpu().numpy(), dw_ref),
         "dw_masked_zero": bool(np.all(dw.cpu().numpy()[dw_ref == 0.0] == 0.0)),
@@ -143,6 +144,64 @@ def test_stream_kernel(IF, shape, monkeypatch):
     g = rng.standard_normal((B, C, H, W)).astype(np.float32)
     w = make_weight(rng, C, C, KH, KW, scale)
     assert_parity(run_all(IF, x, w, g, groups))
+
+
+ORIENT_SHAPES = [(3, 12, 16, 16, 3, 3, 1, 0.02), (2, 8, 7, 7, 2, 2, 4, 0.05), (2, 3, 9, 13, 3, 3, 1, 0.1),
+                 (2, 5, 13, 9, 2, 3, 1, 0.1), (4, 1, 28, 28, 3, 3, 1, 0.1), (2, 4, 6, 6, 5, 5, 1, 0.02),
+                 (3, 20, 10, 10, 3, 3, 1, 0.02)]
+
+
+@pytest.mark.parametrize("kernel", ["resident", "stream", "global"])
+@pytest.mark.parametrize("orient", ["TR", "BL", "BR"])
+@pytest.mark.parametrize("shape", ORIENT_SHAPES, ids=lambda s: "x".join(map(str, s[:7])))
+def test_orientations_by_index_reflection(IF, shape, orient, kernel, monkeypatch):
+    """ifk_problem.orient: every operator in the frame reflected along the order's axes, against
+    the oracle applied to explicitly flipped copies (what the reference layers do with torch.flip,
+    inf/layers/inv_conv.py:198-214) -- for each of the three solve kernels."""
+    if kernel == "stream":
+        if shape[1] // shape[6] == 1:
+            pytest.skip("single-channel groups have no stream variant")
+        monkeypatch.setenv("IFK_SOLVE_STREAM", "1")
+    elif kernel == "global":
+        monkeypatch.setenv("IFK_SOLVE_GLOBAL", "1")
+    B, C, H, W, KH, KW, groups, scale = shape
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, KH, KW, scale)
+    assert_parity(run_all(IF, x, w, g, groups, orient=orient))
+
+
+def test_bad_orient_is_rejected(IF):
+    x = torch.randn(1, 4, 5, 5, device="cuda")
+    w = torch.zeros(4, 4, 3, 3, device="cuda")
+    with pytest.raises(ValueError):
+        IF.inverse(x, w, groups=1, orient=7)
+    with pytest.raises(ValueError):
+        IF.conv(x, w, groups=1, orient="XX")
+
+
+def test_layer_orders_match_autograd_through_flips():
+    """order='TR'/'BL'/'BR' forward, dX and dW equal the top-left op wrapped in torch.flip"""
+    from inverse_flow_b200.layers import inv_flow_with_pad
+    from inverse_flow_b200.layers.inv_conv import inv_conv_4d
+    flips = {"TR": [3], "BL": [2], "BR": [2, 3]}
+    for order, dims in flips.items():
+        torch.manual_seed(5)
+        m = inv_flow_with_pad(8, 8, (3, 3), order=order, groups=1).to("cuda")
+        x = torch.randn(3, 8, 9, 7, device="cuda", requires_grad=True)
+        g = torch.randn(3, 8, 9, 7, device="cuda")
+        y, _ = m(x)
+        y.backward(g)
+        dx, dw = x.grad.clone(), m.weight_fwd.grad.clone()
+        x2 = x.detach().clone().requires_grad_(True)
+        w2 = m.weight_fwd.detach().clone().requires_grad_(True)
+        y2 = torch.flip(inv_conv_4d(torch.flip(x2, dims), w2, 1), dims)
+        y2.backward(g)
+        for a, b in ((y, y2), (dx, x2.grad), (dw, w2.grad)):
+            assert oracle.max_rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy().astype(np.float64)) < TOL
+        rec = m.reverse(y.detach())
+        assert oracle.max_rel_err(rec.cpu().numpy(), x.detach().cpu().numpy().astype(np.float64)) < TOL
 
 
 def test_large_images_take_the_stream_path(IF):
