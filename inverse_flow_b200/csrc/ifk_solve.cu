@@ -96,7 +96,10 @@ static SolveConfig choose_config(const Geometry &g)
     if (best.grid_x < 1) best.grid_x = 1;
     const char *force_global = getenv("IFK_SOLVE_GLOBAL");      // testing: the plain fallback kernel
     const char *force_stream = getenv("IFK_SOLVE_STREAM");      // testing: the stream kernel
-    if ((force_global && force_global[0] == '1') || (force_stream && force_stream[0] == '1')) return best;
+    const char *force_window = getenv("IFK_SOLVE_WINDOW");      // testing: the window kernel
+    if ((force_global && force_global[0] == '1') || (force_stream && force_stream[0] == '1') ||
+        (force_window && force_window[0] == '1'))
+        return best;
 
     const int HP = g.H + g.KH - 1, WP = g.W + g.KW - 1;
     const int XN = round_up(g.Cg * g.H * g.W, 4);
@@ -202,6 +205,20 @@ bool solve_use_pdl()
     return !(e && e[0] == '0');
 }
 
+// which kernel serves an image that is not shared-memory resident: 2 = window (ring of diagonals
+// in shared memory), 1 = stream (neighbours through L1/L2; rings that exceed shared memory),
+// 0 = the plain fallback.  IFK_SOLVE_GLOBAL / IFK_SOLVE_STREAM = 1 pin the older kernels (tests).
+static int large_image_kernel(const Geometry &g)
+{
+    const char *force_global = getenv("IFK_SOLVE_GLOBAL");
+    if (force_global && force_global[0] == '1') return 0;
+    const char *force_stream = getenv("IFK_SOLVE_STREAM");
+    const bool pin_stream = force_stream && force_stream[0] == '1';
+    if (!pin_stream && window_solve_available(g)) return 2;
+    if (stream_solve_available(g)) return 1;
+    return 0;
+}
+
 static long long *g_probe = nullptr;   // tuning aid, see ifk_debug_set_probe
 void set_solve_probe(long long *p) { g_probe = p; }
 
@@ -218,9 +235,10 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
     p.probe = g_probe;
     dim3 grid(c.grid_x, g.groups);
     if (!c.smem) {
-        const char *force_global = getenv("IFK_SOLVE_GLOBAL");
-        if (!(force_global && force_global[0] == '1') && stream_solve_available(g))
-            return launch_solve_stream(g, in, prep_dir, out, reverse, s);
+        switch (large_image_kernel(g)) {
+            case 2: return launch_solve_window(g, in, prep_dir, out, reverse, s);
+            case 1: return launch_solve_stream(g, in, prep_dir, out, reverse, s);
+        }
         solve_global_kernel<<<grid, c.threads, 0, s>>>(p);
         return cuda_status(cudaGetLastError());
     }
@@ -247,9 +265,10 @@ int describe_solve(const Geometry &g, char *buf, size_t buflen)
         snprintf(buf, buflen, "smem<cc=%d,nv=%d,vec=%d> ns=%d nct=%d slots=%d iters=%d threads=%d(%d) smem=%zuB grid=%dx%d",
                  c.cc, c.nv, c.vec, c.ns, c.nct, c.nslots, c.iters, c.threads, c.nwork, c.smem_bytes, c.grid_x, g.groups);
     else {
-        const char *force_global = getenv("IFK_SOLVE_GLOBAL");
-        if (!(force_global && force_global[0] == '1') && stream_solve_available(g))
-            return describe_stream_solve(g, buf, buflen);
+        switch (large_image_kernel(g)) {
+            case 2: return describe_window_solve(g, buf, buflen);
+            case 1: return describe_stream_solve(g, buf, buflen);
+        }
         snprintf(buf, buflen, "global threads=%d grid=%dx%d", c.threads, c.grid_x, g.groups);
     }
     return 0;

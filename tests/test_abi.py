@@ -115,10 +115,18 @@ def test_batched_entry_points_validate_arguments(lib):
     assert lib.ifk_prepare_many_f32(ctypes.byref(bad), 1, dummy, 0, dummy, 0, None) == -3
 
 
-def test_describe_solve_variants(lib):
-    """resident kernel for model shapes, stream kernel (with and without a cluster) for images beyond
-    shared memory, plain fallback only where the reduction slice exceeds the register budget"""
+def test_describe_solve_variants(lib, monkeypatch):
+    """resident kernel for model shapes; the window kernel (ring of diagonals in shared memory, with
+    and without a cluster) for images beyond shared memory; the older stream kernel where even the
+    ring does not fit; the plain fallback only where neither registers nor clusters hold the weights"""
     d = lambda *a: _native.describe_solve(_native.problem(*a))
-    assert d(64, 12, 64, 64, 3, 3, 12, 1).startswith("stream<") and "cluster=1" in d(64, 12, 64, 64, 3, 3, 12, 1)
-    assert "cluster=4" in d(8, 96, 32, 32, 3, 3, 96, 1)
-    assert d(8, 48, 16, 16, 5, 5, 48, 1).startswith("global")
+    assert d(64, 12, 64, 64, 3, 3, 12, 1).startswith("window<") and "cluster=1" in d(64, 12, 64, 64, 3, 3, 12, 1)
+    assert d(8, 96, 32, 32, 3, 3, 96, 1).startswith("window<") and "cluster=4" in d(8, 96, 32, 32, 3, 3, 96, 1)
+    assert d(8, 48, 16, 16, 5, 5, 48, 1).startswith("window<") and "cluster=2" in d(8, 48, 16, 16, 5, 5, 48, 1)
+    assert d(8, 96, 128, 128, 3, 3, 96, 1).startswith("stream<")
+    assert d(8, 96, 64, 64, 7, 7, 96, 1).startswith("global")
+    monkeypatch.setenv("IFK_SOLVE_STREAM", "1")
+    assert d(64, 12, 64, 64, 3, 3, 12, 1).startswith("stream<")
+    monkeypatch.delenv("IFK_SOLVE_STREAM")
+    monkeypatch.setenv("IFK_SOLVE_WINDOW", "1")
+    assert d(3, 12, 16, 16, 3, 3, 12, 1).startswith("window<")

@@ -151,7 +151,7 @@ ORIENT_SHAPES = [(3, 12, 16, 16, 3, 3, 1, 0.02), (2, 8, 7, 7, 2, 2, 4, 0.05), (2
                  (3, 20, 10, 10, 3, 3, 1, 0.02)]
 
 
-@pytest.mark.parametrize("kernel", ["resident", "stream", "global"])
+@pytest.mark.parametrize("kernel", ["resident", "window", "stream", "global"])
 @pytest.mark.parametrize("orient", ["TR", "BL", "BR"])
 @pytest.mark.parametrize("shape", ORIENT_SHAPES, ids=lambda s: "x".join(map(str, s[:7])))
 def test_orientations_by_index_reflection(IF, shape, orient, kernel, monkeypatch):
@@ -162,6 +162,8 @@ def test_orientations_by_index_reflection(IF, shape, orient, kernel, monkeypatch
         if shape[1] // shape[6] == 1:
             pytest.skip("single-channel groups have no stream variant")
         monkeypatch.setenv("IFK_SOLVE_STREAM", "1")
+    elif kernel == "window":
+        monkeypatch.setenv("IFK_SOLVE_WINDOW", "1")
     elif kernel == "global":
         monkeypatch.setenv("IFK_SOLVE_GLOBAL", "1")
     B, C, H, W, KH, KW, groups, scale = shape
@@ -204,11 +206,12 @@ def test_layer_orders_match_autograd_through_flips():
         assert oracle.max_rel_err(rec.cpu().numpy(), x.detach().cpu().numpy().astype(np.float64)) < TOL
 
 
-def test_large_images_take_the_stream_path(IF):
-    """(2,12,64,64) k=3 and (2,48,32,32) k=3 exceed shared memory: stream kernel; dW staged or not."""
+def test_large_images_take_the_window_path(IF):
+    """(2,12,64,64) k=3 and (2,48,32,32) k=3 exceed shared memory: window kernel; dW staged or not."""
     from inverse_flow_b200 import _native
-    for (B, C, H, W, k, scale) in [(2, 12, 64, 64, 3, 0.01), (2, 48, 32, 32, 3, 0.005)]:
-        assert _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1)).startswith("stream<")
+    for (B, C, H, W, k, scale) in [(2, 12, 64, 64, 3, 0.01), (2, 48, 32, 32, 3, 0.005), (3, 3, 128, 96, 3, 0.05),
+                                   (2, 1, 200, 260, 3, 0.05), (3, 12, 64, 48, 5, 0.003)]:
+        assert _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1)).startswith("window<")
         rng = np.random.default_rng(6)
         x = rng.standard_normal((B, C, H, W)).astype(np.float32)
         g = rng.standard_normal((B, C, H, W)).astype(np.float32)
@@ -216,12 +219,17 @@ def test_large_images_take_the_stream_path(IF):
         assert_parity(run_all(IF, x, w, g, 1))
 
 
-def test_wide_group_runs_as_a_thread_block_cluster(IF):
-    """Cg = 96, k = 3: 73.7K prepared weights exceed one SM's register file, so the stream kernel
-    runs as a cluster of CTAs that split the output channels and meet at a cluster barrier."""
+@pytest.mark.parametrize("kernel", ["window", "stream"])
+def test_wide_group_runs_as_a_thread_block_cluster(IF, kernel, monkeypatch):
+    """Cg = 96, k = 3: 73.7K prepared weights exceed one SM's register file, so the large-image
+    kernels run as a cluster of CTAs that split the output channels: the window kernel exchanges y
+    through distributed shared memory, the stream kernel through L2; one cluster barrier per diagonal."""
     from inverse_flow_b200 import _native
+    if kernel == "stream":
+        monkeypatch.setenv("IFK_SOLVE_STREAM", "1")
     B, C, H, W, k = 2, 96, 8, 8, 3
-    assert "cluster=4" in _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1))
+    d = _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1))
+    assert d.startswith(kernel + "<") and "cluster=4" in d
     rng = np.random.default_rng(7)
     x = rng.standard_normal((B, C, H, W)).astype(np.float32)
     g = rng.standard_normal((B, C, H, W)).astype(np.float32)
@@ -229,14 +237,54 @@ def test_wide_group_runs_as_a_thread_block_cluster(IF):
     assert_parity(run_all(IF, x, w, g, 1))
 
 
-def test_large_image_takes_the_global_path(IF):
-    """(2, 48, 32, 32) k=5: neither shared memory nor the register file holds it -> plain fallback."""
-    rng = np.random.default_rng(5)
-    B, C, H, W, k = 2, 48, 32, 32, 5
+@pytest.mark.parametrize("shape", [(3, 48, 16, 16, 5, 5, 0.002, "cluster=2"), (2, 48, 12, 10, 7, 7, 0.001, "cluster=8"),
+                                   (45, 48, 6, 5, 7, 7, 0.001, "cluster=8"),      # 37 clusters: some solve two images
+                                   (2, 96, 16, 16, 5, 5, 0.001, "cluster=16"), (5, 96, 16, 12, 3, 3, 0.003, "cluster=4")],
+                         ids=lambda s: "x".join(map(str, s[:6])))
+def test_wide_groups_with_large_kernels_run_in_clusters(IF, shape):
+    """C >= 48 with k >= 5: the weights only fit the register files of 2..16 SMs together"""
+    from inverse_flow_b200 import _native
+    B, C, H, W, KH, KW, scale, tag = shape
+    d = _native.describe_solve(_native.problem(B, C, H, W, KH, KW, C, 1))
+    assert d.startswith("window<") and tag in d, d
+    rng = np.random.default_rng(17)
     x = rng.standard_normal((B, C, H, W)).astype(np.float32)
     g = rng.standard_normal((B, C, H, W)).astype(np.float32)
-    w = make_weight(rng, C, C, k, k, 0.005)
+    w = make_weight(rng, C, C, KH, KW, scale)
     assert_parity(run_all(IF, x, w, g, 1))
+
+
+def test_large_image_takes_the_global_path(IF):
+    """(2, 96, 20, 20) k=7: neither shared memory nor 16 register files hold it -> plain fallback."""
+    from inverse_flow_b200 import _native
+    rng = np.random.default_rng(5)
+    B, C, H, W, k = 2, 96, 20, 20, 7
+    assert _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1)).startswith("global")
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, k, k, 0.0002)
+    assert_parity(run_all(IF, x, w, g, 1))
+
+
+@pytest.mark.parametrize("shape", [(3, 12, 16, 16, 3, 3, 1, 0.02), (2, 8, 7, 7, 2, 2, 4, 0.05),
+                                   (2, 3, 9, 13, 3, 3, 1, 0.1), (2, 5, 13, 9, 2, 3, 1, 0.1),
+                                   (2, 24, 8, 8, 3, 3, 1, 0.02), (2, 4, 6, 6, 5, 5, 1, 0.02),
+                                   (4, 1, 28, 28, 3, 3, 1, 0.1), (3, 20, 10, 10, 3, 3, 1, 0.02),
+                                   (2, 2, 12, 12, 7, 7, 1, 0.01), (1, 6, 1, 9, 3, 3, 1, 0.1), (1, 6, 9, 1, 3, 3, 1, 0.1),
+                                   (150, 12, 20, 20, 3, 3, 1, 0.02), (700, 4, 9, 7, 3, 3, 1, 0.05),
+                                   (1300, 6, 5, 8, 2, 3, 2, 0.05)],
+                         ids=lambda s: "x".join(map(str, s[:7])))
+def test_window_kernel(IF, shape, monkeypatch):
+    """Force the ring-of-diagonals kernel on small shapes (several images per CTA for the last ones)."""
+    monkeypatch.setenv("IFK_SOLVE_WINDOW", "1")
+    from inverse_flow_b200 import _native
+    B, C, H, W, KH, KW, groups, scale = shape
+    assert _native.describe_solve(_native.problem(B, C, H, W, KH, KW, C, groups)).startswith("window<")
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, KH, KW, scale)
+    assert_parity(run_all(IF, x, w, g, groups))
 
 
 def test_weight_with_fewer_input_columns(IF):

@@ -29,12 +29,24 @@ SWEEP = [
 ]
 
 
+LARGE = [   # sweep cells whose images do not fit in shared memory (window / stream / fallback kernels)
+    (64, 12, 64, 64, 3, 1), (512, 12, 64, 64, 3, 1), (64, 12, 64, 64, 5, 1), (64, 12, 64, 64, 7, 1),
+    (64, 48, 32, 32, 3, 1), (512, 48, 32, 32, 3, 1), (64, 48, 64, 64, 3, 1), (64, 48, 16, 16, 5, 1),
+    (64, 48, 32, 32, 5, 1), (64, 48, 16, 16, 7, 1), (64, 96, 16, 16, 3, 1), (8, 96, 32, 32, 3, 1),
+    (64, 96, 32, 32, 3, 1), (64, 96, 16, 16, 5, 1), (64, 3, 128, 128, 3, 1),
+]
+
+
 def make_weight(C, k, gen):
     w = torch.zeros(C, C, k, k)
     torch.nn.init.dirac_(w)
     w += torch.nn.init.xavier_normal_(torch.empty(C, C, k, k), gain=0.01, generator=gen)
     w[:, -1, -1, -1] = 1.0
     return w
+
+
+def Cg_of(C, g):
+    return C // g
 
 
 def time_op(fn, iters, flush=None, reps=20):
@@ -72,8 +84,12 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default=None)
     ap.add_argument("--flush", action="store_true", help="flush L2 between iterations (cold)")
+    ap.add_argument("--solve-only", action="store_true", help="time the forward solve only")
+    ap.add_argument("--shape", default=None, help="one shape B,C,H,W,k,g instead of a list")
     args = ap.parse_args()
-    shapes = {"model": MODEL, "sweep": SWEEP, "all": MODEL + SWEEP}[args.shapes]
+    shapes = {"model": MODEL, "sweep": SWEEP, "large": LARGE, "all": MODEL + SWEEP}[args.shapes]
+    if args.shape:
+        shapes = [tuple(int(v) for v in args.shape.split(","))]
     gen = torch.Generator().manual_seed(0)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if args.flush else None
     lib = _native.load()
@@ -89,6 +105,17 @@ def main():
         dx = torch.empty_like(x)
         out = torch.empty_like(x)
         dw = torch.empty_like(w)
+        reps = 20 if B * C * H * W * Cg_of(C, g) * k * k < 2e10 else 2
+        if args.solve_only:
+            t_inv = time_op(lambda: IF.inverse(x, w, out=out, prepared=prep), args.iters, flush, reps)
+            N = B * C * H * W
+            flops = 2 * N * (C // g * k * k - 1)
+            desc = _native.describe_solve(_native.problem(B, C, H, W, k, k, C, g))
+            rows.append(dict(shape=[B, C, H, W, k, g], us=dict(inverse=t_inv), inverse_GFLOPs=flops / t_inv / 1e3,
+                             inverse_images_per_s=B / (t_inv * 1e-6), variant=desc))
+            print("%-28s inverse %10.1f us %9.1f GFLOP/s  %s" % (str((B, C, H, W, k, g)), t_inv, flops / t_inv / 1e3, desc),
+                  flush=True)
+            continue
         t_prep = time_op(lambda: IF.Prepared(w, g), args.iters, flush)
         t_inv = time_op(lambda: IF.inverse(x, w, out=out, prepared=prep), args.iters, flush)
         t_dx = time_op(lambda: IF.bwd_input(grad, w, out=dx, prepared=prep), args.iters, flush)
