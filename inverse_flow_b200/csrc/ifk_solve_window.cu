@@ -83,48 +83,60 @@ __device__ __forceinline__ void sts_cluster_all(uint32_t addr, float v, int csiz
     }
 }
 
-// reduce-scatter as Rs (ifk_solve_kernel.cuh); the finishing lane adds z, writes the ring and HBM
-template <int N, int LEVELS, bool CL>
+// reduce-scatter as Rs (ifk_solve_kernel.cuh) for RP independent pixels at once (their shuffles
+// interleave); the finishing lane adds z, writes the ring and HBM
+template <int N, int LEVELS, bool CL, int RP>
 struct RsWin {
-    __device__ __forceinline__ static void run(float *acc, const float *zv, int ks, int m, int own_size,
-                                               bool active, uint32_t ya, float *gp, int gstride, int csize)
+    __device__ __forceinline__ static void run(float (*acc)[N], float (*zv)[N], int ks, int m, int own_size,
+                                               const bool *active, const uint32_t *ya, float *const *gp, int gstride,
+                                               int csize)
     {
+        static_assert(LEVELS >= 0, "");
         if (m == 0 || LEVELS == 0) {
 #pragma unroll
-            for (int i = 0; i < N; i++)
-                if (active && i < own_size) {
-                    const float yv = acc[i] + zv[i];
-                    if (CL) sts_cluster_all(ya + 4u * i, yv, csize);
-                    else sts_f32(ya + 4u * i, yv);
-                    gp[(size_t)i * gstride] = yv;
-                }
+            for (int r = 0; r < RP; r++)
+#pragma unroll
+                for (int i = 0; i < N; i++)
+                    if (active[r] && i < own_size) {
+                        const float yv = acc[r][i] + zv[r][i];
+                        if (CL) sts_cluster_all(ya[r] + 4u * i, yv, csize);
+                        else sts_f32(ya[r] + 4u * i, yv);
+                        gp[r][(size_t)i * gstride] = yv;
+                    }
             return;
         }
         constexpr int HALF = (N + 1) / 2;
         const bool hi = (ks & m) != 0;
+        float nxt[RP][HALF], nz[RP][HALF];
 #pragma unroll
-        for (int i = 0; i < HALF; i++) {
-            const float lo_v = acc[i];
-            const float hi_v = (i + HALF < N) ? acc[i + HALF] : 0.f;
-            acc[i] = (hi ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, hi ? lo_v : hi_v, m);
-        }
-        RsWin<HALF, (LEVELS > 0 ? LEVELS - 1 : 0), CL>::run(acc, zv, ks, m >> 1, own_size, active, ya, gp, gstride,
-                                                           csize);
+        for (int r = 0; r < RP; r++)
+#pragma unroll
+            for (int i = 0; i < HALF; i++) {
+                const float lo_v = acc[r][i];
+                const float hi_v = (i + HALF < N) ? acc[r][i + HALF] : 0.f;
+                nxt[r][i] = (hi ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, hi ? lo_v : hi_v, m);
+                nz[r][i] = zv[r][i];
+            }
+        RsWin<HALF, (LEVELS > 0 ? LEVELS - 1 : 0), CL, RP>::run(nxt, nz, ks, m >> 1, own_size, active, ya, gp, gstride,
+                                                               csize);
     }
 };
 
-template <int CC, int NV, int VEC>
+template <int CC, int NV, int VEC, int RP>
 constexpr int window_max_threads()
 {
-    // CC*NV*VEC weights + NV*VEC loaded values + NV offsets + packed slot phases + sums + bookkeeping
-    int regs = CC * NV * VEC + NV * VEC + NV + (NV + 7) / 8 + 3 * CC + 56;
+    // CC*NV*VEC weights + per pixel in flight (NV*VEC loaded values + sums) + NV offsets + packed slot
+    // phases + bookkeeping
+    int regs = CC * NV * VEC + RP * (NV * VEC + 3 * CC) + NV + (NV + 7) / 8 + 68;
     if (regs > 255) regs = 255;
     int t = (65536 / regs) / 32 * 32;
     return t > 1024 ? 1024 : t;
 }
 
-template <int CC, int NV, int VEC, bool CL>
-__global__ void __launch_bounds__(window_max_threads<CC, NV, VEC>())
+// RP = rows a thread keeps in flight per step: with a single row slot per CTA (wide groups) a step is
+// one long dependent chain (loads -> FMAs -> shuffles -> stores); two independent pixels interleave
+template <int CC, int NV, int VEC, bool CL, int RP>
+__global__ void __launch_bounds__(window_max_threads<CC, NV, VEC, RP>())
 solve_window_kernel(const WindowParams p)
 {
     extern __shared__ __align__(16) float smem[];
@@ -222,8 +234,8 @@ solve_window_kernel(const WindowParams p)
             const int c4 = i / HW, r = i - c4 * HW;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             const float *tp = tT + c4 * 4;
-#pragma unroll 4
-            for (int ci = 0; ci < Cg; ci++) {
+#pragma unroll 8
+            for (int ci = 0; ci < Cg; ci++) {          // 8 loads in flight per thread: the pre-pass is latency bound
                 const float xv = __ldg(in_b + (size_t)ci * HW + r);
                 const float4 t4 = *reinterpret_cast<const float4 *>(tp + ci * p.CgP4);
                 a0 = fmaf(t4.x, xv, a0);
@@ -278,36 +290,52 @@ solve_window_kernel(const WindowParams p)
                 float *gp = gp_d;
                 int col = d - srow;
 #pragma unroll 1
-                for (int it = 0; it < p.iters; it++, radd += row_step, gp += g_row, col -= p.nslots) {
-                    const bool active = worker && srow + it * p.nslots < H && (unsigned)col < (unsigned)W;
-                    if (!__any_sync(0xffffffffu, active)) continue;        // warp-uniform
-                    const uint32_t ra = active ? radd : 0u;                // idle lanes: a legal row
-                    float v[NV * VEC];
+                for (int it = 0; it < p.iters; it += RP, radd += RP * row_step, gp += RP * g_row, col -= RP * p.nslots) {
+                    bool active[RP];
+                    uint32_t ya[RP];
+                    float *gpp[RP];
+                    bool any = false;
 #pragma unroll
-                    for (int j = 0; j < NV; j++) lds_vec<VEC>(v + j * VEC, offs[j] + ra);
-                    float zv[CC];
-#pragma unroll
-                    for (int i = 0; i < CC; i++) zv[i] = (active && i < own_size) ? lds_f32(ya_d + ra + 4u * i) : 0.f;
-
-                    constexpr int NACC = CC >= 4 ? 1 : (CC >= 2 ? 2 : 4);  // independent FMA chains
-                    float part[NACC][CC];
-#pragma unroll
-                    for (int a = 0; a < NACC; a++)
-#pragma unroll
-                        for (int cc = 0; cc < CC; cc++) part[a][cc] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < NV * VEC; i++)
-#pragma unroll
-                        for (int cc = 0; cc < CC; cc++)
-                            part[i % NACC][cc] = fmaf(wreg[cc][i], v[i], part[i % NACC][cc]);
-                    float acc[CC];
-#pragma unroll
-                    for (int cc = 0; cc < CC; cc++) {
-                        acc[cc] = part[0][cc];
-#pragma unroll
-                        for (int a = 1; a < NACC; a++) acc[cc] += part[a][cc];
+                    for (int r = 0; r < RP; r++) {
+                        active[r] = worker && it + r < p.iters && srow + (it + r) * p.nslots < H &&
+                                    (unsigned)(col - r * p.nslots) < (unsigned)W;
+                        any |= active[r];
                     }
-                    RsWin<CC, 5, CL>::run(acc, zv, ks, NS >> 1, own_size, active, ya_d + ra, gp, HW, p.csize);
+                    if (!__any_sync(0xffffffffu, any)) continue;           // warp-uniform
+                    float v[RP][NV * VEC];
+                    float zv[RP][CC];
+#pragma unroll
+                    for (int r = 0; r < RP; r++) {
+                        const uint32_t ra = active[r] ? radd + r * row_step : 0u;   // idle lanes: a legal row
+                        ya[r] = ya_d + ra;
+                        gpp[r] = gp + r * g_row;
+#pragma unroll
+                        for (int j = 0; j < NV; j++) lds_vec<VEC>(v[r] + j * VEC, offs[j] + ra);
+#pragma unroll
+                        for (int i = 0; i < CC; i++) zv[r][i] = (active[r] && i < own_size) ? lds_f32(ya[r] + 4u * i) : 0.f;
+                    }
+                    constexpr int NACC = (CC >= 4 || RP > 1) ? 1 : (CC >= 2 ? 2 : 4);  // independent FMA chains
+                    float acc[RP][CC];
+#pragma unroll
+                    for (int r = 0; r < RP; r++) {
+                        float part[NACC][CC];
+#pragma unroll
+                        for (int a = 0; a < NACC; a++)
+#pragma unroll
+                            for (int cc = 0; cc < CC; cc++) part[a][cc] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < NV * VEC; i++)
+#pragma unroll
+                            for (int cc = 0; cc < CC; cc++)
+                                part[i % NACC][cc] = fmaf(wreg[cc][i], v[r][i], part[i % NACC][cc]);
+#pragma unroll
+                        for (int cc = 0; cc < CC; cc++) {
+                            acc[r][cc] = part[0][cc];
+#pragma unroll
+                            for (int a = 1; a < NACC; a++) acc[r][cc] += part[a][cc];
+                        }
+                    }
+                    RsWin<CC, 5, CL, RP>::run(acc, zv, ks, NS >> 1, own_size, active, ya, gpp, HW, p.csize);
                 }
             } else {
                 stage(d + kWinPF, sn);
@@ -344,23 +372,25 @@ solve_window_kernel(const WindowParams p)
 // ---- host side -----------------------------------------------------------------------------
 struct WindowConfig {
     bool ok;
-    int cc, nv, vec, ns, nct, nslots, iters, threads, nwork, nio, grid_x;
+    int cc, nv, vec, rp, ns, nct, nslots, iters, threads, nwork, nio, grid_x;
     int csize, CgV, NVT, PS, HPr, S;
     size_t smem_bytes;
 };
 
+// X(CC, NV, RP)
 #define IFK_WINDOW_VARIANTS_V4                                                                       \
-    X(12, 3) X(8, 3) X(6, 3) X(4, 3) X(8, 5) X(6, 5) X(4, 5) X(6, 6) X(4, 6) X(3, 6)                \
-    X(4, 9) X(3, 9) X(2, 9) X(2, 12) X(1, 12) X(1, 18)
+    X(12, 3, 1) X(8, 3, 1) X(6, 3, 1) X(4, 3, 1) X(8, 5, 1) X(6, 5, 1) X(4, 5, 1) X(6, 6, 1) X(4, 6, 1)        \
+    X(3, 6, 1) X(4, 9, 1) X(3, 9, 1) X(2, 9, 1) X(2, 12, 1) X(1, 12, 1) X(1, 18, 1)                             \
+    X(8, 3, 2) X(6, 3, 2) X(4, 3, 2) X(4, 5, 2) X(4, 6, 2) X(3, 6, 2) X(2, 9, 2) X(1, 12, 2)
 #define IFK_WINDOW_VARIANTS_V1                                                                       \
-    X(1, 8) X(1, 12) X(1, 24) X(3, 6) X(3, 12) X(3, 24) X(2, 6) X(2, 12)
+    X(1, 8, 1) X(1, 12, 1) X(1, 24, 1) X(3, 6, 1) X(3, 12, 1) X(3, 24, 1) X(2, 6, 1) X(2, 12, 1)
 
-static int window_variant_threads(int cc, int nv, int vec)
+static int window_variant_threads(int cc, int nv, int vec, int rp)
 {
-#define X(CC, NV) if (vec == 4 && cc == CC && nv == NV) return window_max_threads<CC, NV, 4>();
+#define X(CC, NV, RP) if (vec == 4 && cc == CC && nv == NV && rp == RP) return window_max_threads<CC, NV, 4, RP>();
     IFK_WINDOW_VARIANTS_V4
 #undef X
-#define X(CC, NV) if (vec == 1 && cc == CC && nv == NV) return window_max_threads<CC, NV, 1>();
+#define X(CC, NV, RP) if (vec == 1 && cc == CC && nv == NV && rp == RP) return window_max_threads<CC, NV, 1, RP>();
     IFK_WINDOW_VARIANTS_V1
 #undef X
     return 0;
@@ -381,13 +411,13 @@ static WindowConfig choose_window(const Geometry &g)
     const size_t smem = ((size_t)g.Cg * round_up(g.Cg, 4) + (size_t)round_up(S * HPr * PS, 4)) * sizeof(float);
     if (smem > (size_t)kMaxSmemBytes) return best;
     double best_cost = 1e30;
-    int fcc = 0, fnv = 0, fcs = 0;
-    if (const char *e = getenv("IFK_WINDOW_CFG")) sscanf(e, "%d,%d,%d", &fcc, &fnv, &fcs);   // tuning only
+    int fcc = 0, fnv = 0, fcs = 0, frp = 0;
+    if (const char *e = getenv("IFK_WINDOW_CFG")) sscanf(e, "%d,%d,%d,%d", &fcc, &fnv, &fcs, &frp);   // tuning only
     static const int kCCs[] = {12, 8, 6, 4, 3, 2, 1};
     static const int kNVs[] = {3, 5, 6, 8, 9, 12, 18, 24};
     static const int kCsizes[] = {1, 2, 4, 8, 16};
+    const int ndiag = g.H + g.W - 1;
     for (int csize : kCsizes) {
-        if (best.ok && !fcs) break;                  // smallest cluster that holds the weights wins
         if (fcs && csize != fcs) continue;
         if (csize > 1 && vec != 4) continue;
         for (int cc : kCCs) {
@@ -395,41 +425,76 @@ static WindowConfig choose_window(const Geometry &g)
             const int nct_total = (g.Cg + cc - 1) / cc;
             if (csize > nct_total) continue;
             const int nct = (nct_total + csize - 1) / csize;
-            for (int nv : kNVs) {
-                const int tmax = window_variant_threads(cc, nv, vec);
-                if (tmax == 0) continue;
-                if (fcc && (cc != fcc || nv != fnv)) continue;
-                for (int ns = 1; ns <= 32; ns *= 2) {
-                    if ((long)ns * nv < NVT) continue;
-                    if (ns > 1 && (long)(ns / 2) * nv >= NVT) continue;
-                    const int per_slot = ns * nct;
-                    const int nio = 64;
-                    if (per_slot + nio > tmax) continue;
-                    int nslots = (tmax - nio) / per_slot;
-                    if (nslots > g.H) nslots = g.H;
-                    const int iters = (g.H + nslots - 1) / nslots;
-                    nslots = (g.H + iters - 1) / iters;              // same passes, fewer idle slots
-                    const int nwork = round_up(nslots * per_slot, 32);
-                    if (nwork + nio > tmax) continue;
-                    const double waste = (double)(ns * nv) / NVT * (double)(nct * csize * cc) / g.Cg;
-                    const double step = nv * (2.0 + cc * vec) + 6.0 * cc + 90.0;
-                    const double cost = iters * step * waste * (1.0 + 0.1 * (nwork / 128)) + (csize > 1 ? 400.0 : 60.0);
-                    if (cost < best_cost) {
-                        best_cost = cost;
-                        best.ok = true;
-                        best.cc = cc; best.nv = nv; best.vec = vec; best.ns = ns; best.nct = nct;
-                        best.nslots = nslots; best.iters = iters; best.nwork = nwork; best.nio = nio;
-                        best.threads = nwork + nio; best.csize = csize;
+            for (int nv : kNVs)
+                for (int rp = 1; rp <= 2; rp++) {
+                    const int tmax = window_variant_threads(cc, nv, vec, rp);
+                    if (tmax == 0) continue;
+                    if (fcc && (cc != fcc || nv != fnv)) continue;
+                    if (frp && rp != frp) continue;
+                    for (int ns = 1; ns <= 32; ns *= 2) {
+                        if ((long)ns * nv < NVT) continue;
+                        if (ns > 1 && (long)(ns / 2) * nv >= NVT) continue;
+                        const int per_slot = ns * nct;
+                        const int nio = 64;
+                        if (per_slot + nio > tmax) continue;
+                        int nslots = (tmax - nio) / per_slot;
+                        if (nslots > g.H) nslots = g.H;
+                        const int iters = (g.H + nslots - 1) / nslots;
+                        nslots = (g.H + iters - 1) / iters;              // same passes, fewer idle slots
+                        if (rp > 1 && iters < 2) continue;
+                        const int nwork = round_up(nslots * per_slot, 32);
+                        if (nwork + nio > tmax) continue;
+                        // Cycles per image, fitted to tools/tune_window.sh runs.  A step (one row per slot, RP
+                        // of them interleaved) takes the longer of its dependent chain -- loads, FMAs, shuffle
+                        // levels, stores: ~400 + 19 log2(ns) + 1.9 FMAs per thread -- and of what the SM can
+                        // issue for the nslots pixels in flight (instructions / 4 schedulers + ~12 cycles per
+                        // warp-wide 128-bit gather).  A cluster adds its remote stores (~10 cycles each).
+                        int lg = 0;
+                        while ((1 << (lg + 1)) <= ns) lg++;
+                        const double fmas = (double)cc * nv * vec;
+                        const int red = ns > 1 ? 2 * cc : 0;
+                        const double instr = nv * (2.0 + cc * vec) + 2.5 * red + 3.0 * cc + 40.0;
+                        const double pixel = per_slot / 32.0 * (instr / 4.0 + nv * (vec == 4 ? 12.0 : 3.0));
+                        const double chain = 400.0 + 19.0 * lg + 1.9 * fmas;
+                        const double chain_rp = rp == 1 ? chain : 1.6 * chain;    // two pixels: measured 0.8x-0.97x per pixel
+                        const double tp = (double)rp * nslots * pixel;
+                        const double step = chain_rp > tp ? chain_rp : tp;
+                        const double waste = (double)(ns * nv) / NVT * (double)(nct * csize * cc) / g.Cg;
+                        const double exchange = csize > 1 ? 400.0 + 5.0 * g.H * g.Cg * (1.0 + 0.1 * csize) : 60.0;
+                        const double prepass = (double)g.H * g.W * ((g.Cg + 3) / 4) / (nwork + nio) * ((g.Cg + 7) / 8) * 700.0 /
+                                               (csize > 1 ? csize : 1);
+                        const double per_image = ndiag * (((iters + rp - 1) / rp) * step * (1.0 + 0.05 * (waste - 1.0)) + exchange) +
+                                                 prepass;
+                        int per_sm = (int)((size_t)(kMaxSmemBytes + 1024) / (smem + 1024));     // CTAs one SM can hold
+                        if (per_sm > tmax / (nwork + nio)) per_sm = tmax / (nwork + nio);        // register file
+                        if (per_sm > 4) per_sm = 4;
+                        if (per_sm < 1) per_sm = 1;
+                        const long images = (long)(g.B > 0 ? g.B : 1) * g.groups;
+                        const long ctas = images * csize;
+                        const int want = (int)((ctas + kNumSM - 1) / kNumSM);
+                        const int share = want < per_sm ? want : per_sm;
+                        const long resident = (long)kNumSM * share / csize > 0 ? (long)kNumSM * share / csize : 1;
+                        const double waves = (double)((images + resident - 1) / resident);
+                        // CTAs sharing an SM share its issue slots: a wave of them takes longer than one alone
+                        // (two rows in flight also hide the remote-store latency of a cluster: measured 0.8x)
+                        const double cost = per_image * waves * (1.0 + 0.6 * (share - 1)) * (rp > 1 ? (csize > 1 ? 0.85 : 0.95) : 1.0);
+                        if (cost < best_cost) {
+                            best_cost = cost;
+                            best.ok = true;
+                            best.cc = cc; best.nv = nv; best.vec = vec; best.rp = rp; best.ns = ns; best.nct = nct;
+                            best.nslots = nslots; best.iters = iters; best.nwork = nwork; best.nio = nio;
+                            best.threads = nwork + nio; best.csize = csize;
+                        }
                     }
                 }
-            }
         }
     }
     if (!best.ok) return best;
     best.CgV = CgV; best.NVT = NVT; best.PS = PS; best.HPr = HPr; best.S = S;
     best.smem_bytes = smem;
     int per_sm = (int)((size_t)(kMaxSmemBytes + 1024) / (smem + 1024));
-    if (per_sm > 2048 / best.threads) per_sm = 2048 / best.threads;
+    const int tmax_best = window_variant_threads(best.cc, best.nv, best.vec, best.rp);
+    if (per_sm > tmax_best / best.threads) per_sm = tmax_best / best.threads;
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     int nclusters = (kNumSM * per_sm / best.csize + g.groups - 1) / g.groups;
@@ -445,8 +510,8 @@ int describe_window_solve(const Geometry &g, char *buf, size_t buflen)
 {
     const WindowConfig c = choose_window(g);
     snprintf(buf, buflen,
-             "window<cc=%d,nv=%d,vec=%d> cluster=%d ns=%d nct=%d slots=%d iters=%d threads=%d+%d ring=%dx%dx%d smem=%zuB grid=%dx%d",
-             c.cc, c.nv, c.vec, c.csize, c.ns, c.nct, c.nslots, c.iters, c.nwork, c.nio, c.S, c.HPr, c.PS,
+             "window<cc=%d,nv=%d,vec=%d,rp=%d> cluster=%d ns=%d nct=%d slots=%d iters=%d threads=%d+%d ring=%dx%dx%d smem=%zuB grid=%dx%d",
+             c.cc, c.nv, c.vec, c.rp, c.csize, c.ns, c.nct, c.nslots, c.iters, c.nwork, c.nio, c.S, c.HPr, c.PS,
              c.smem_bytes, c.grid_x, g.groups);
     return 0;
 }
@@ -493,15 +558,15 @@ int launch_solve_window(const Geometry &g, const float *in, const float *prep_di
         }                                                                                                 \
         return cuda_status(cudaLaunchKernelEx(&cfg, kern, p));                                            \
     }
-#define X(CC, NV)                                                                                         \
-    if (c.vec == 4 && c.cc == CC && c.nv == NV) {                                                         \
-        if (c.csize > 1) IFK_LAUNCH((solve_window_kernel<CC, NV, 4, true>))                               \
-        else IFK_LAUNCH((solve_window_kernel<CC, NV, 4, false>))                                          \
+#define X(CC, NV, RP)                                                                                     \
+    if (c.vec == 4 && c.cc == CC && c.nv == NV && c.rp == RP) {                                           \
+        if (c.csize > 1) IFK_LAUNCH((solve_window_kernel<CC, NV, 4, true, RP>))                           \
+        else IFK_LAUNCH((solve_window_kernel<CC, NV, 4, false, RP>))                                      \
     }
     IFK_WINDOW_VARIANTS_V4
 #undef X
-#define X(CC, NV)                                                                                         \
-    if (c.vec == 1 && c.cc == CC && c.nv == NV) IFK_LAUNCH((solve_window_kernel<CC, NV, 1, false>))
+#define X(CC, NV, RP)                                                                                     \
+    if (c.vec == 1 && c.cc == CC && c.nv == NV && c.rp == RP) IFK_LAUNCH((solve_window_kernel<CC, NV, 1, false, RP>))
     IFK_WINDOW_VARIANTS_V1
 #undef X
 #undef IFK_LAUNCH

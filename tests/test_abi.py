@@ -121,8 +121,11 @@ def test_describe_solve_variants(lib, monkeypatch):
     ring does not fit; the plain fallback only where neither registers nor clusters hold the weights"""
     d = lambda *a: _native.describe_solve(_native.problem(*a))
     assert d(64, 12, 64, 64, 3, 3, 12, 1).startswith("window<") and "cluster=1" in d(64, 12, 64, 64, 3, 3, 12, 1)
-    assert d(8, 96, 32, 32, 3, 3, 96, 1).startswith("window<") and "cluster=4" in d(8, 96, 32, 32, 3, 3, 96, 1)
-    assert d(8, 48, 16, 16, 5, 5, 48, 1).startswith("window<") and "cluster=2" in d(8, 48, 16, 16, 5, 5, 48, 1)
+    csize = lambda text: int(re.search(r"cluster=(\d+)", text).group(1))
+    # weights beyond one SM's register file: a cluster; wider when the batch leaves SMs idle
+    assert d(8, 96, 32, 32, 3, 3, 96, 1).startswith("window<") and csize(d(8, 96, 32, 32, 3, 3, 96, 1)) >= 4
+    assert d(512, 96, 32, 32, 3, 3, 96, 1).startswith("window<") and csize(d(512, 96, 32, 32, 3, 3, 96, 1)) == 4
+    assert d(512, 48, 16, 16, 5, 5, 48, 1).startswith("window<") and csize(d(512, 48, 16, 16, 5, 5, 48, 1)) == 2
     assert d(8, 96, 128, 128, 3, 3, 96, 1).startswith("stream<")
     assert d(8, 96, 64, 64, 7, 7, 96, 1).startswith("global")
     monkeypatch.setenv("IFK_SOLVE_STREAM", "1")
