@@ -47,6 +47,10 @@ bool window_solve_available(const Geometry &g);
 int describe_window_solve(const Geometry &g, char *buf, size_t buflen);
 int launch_solve_window(const Geometry &g, const float *in, const float *prep_dir, float *out, bool reverse,
                         cudaStream_t s);
+bool shfl_solve_available(const Geometry &g);
+int describe_shfl_solve(const Geometry &g, char *buf, size_t buflen);
+int launch_solve_shfl(const Geometry &g, const float *in, const float *prep_dir, float *out, bool reverse,
+                      cudaStream_t s);
 void set_solve_probe(long long *device_buffer);
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }

@@ -226,6 +226,7 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
                  bool reverse, cudaStream_t s)
 {
     if (g.B == 0) return 0;
+    if (shfl_solve_available(g)) return launch_solve_shfl(g, in, prep_dir, out, reverse, s);
     const SolveConfig c = choose_config(g);
     SolveParams p{};
     p.in = in; p.out = out; p.prep = prep_dir;
@@ -260,6 +261,7 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
 
 int describe_solve(const Geometry &g, char *buf, size_t buflen)
 {
+    if (shfl_solve_available(g)) return describe_shfl_solve(g, buf, buflen);
     const SolveConfig c = choose_config(g);
     if (c.smem)
         snprintf(buf, buflen, "smem<cc=%d,nv=%d,vec=%d> ns=%d nct=%d slots=%d iters=%d threads=%d(%d) smem=%zuB grid=%dx%d",

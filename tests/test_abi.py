@@ -90,12 +90,17 @@ def test_empty_batch_is_a_noop_on_the_solve(lib):
     assert lib.ifk_conv_f32(ctypes.byref(p), None, dummy, None, None) == 0
 
 
-def test_describe_solve_picks_the_resident_kernel_for_model_shapes(lib):
-    for shape in [(100, 4, 14, 14, 2), (100, 8, 7, 7, 2), (64, 1, 28, 28, 3), (100, 12, 16, 16, 3),
-                  (100, 24, 8, 8, 3), (100, 48, 4, 4, 3)]:
+def test_describe_solve_picks_the_on_chip_kernels_for_model_shapes(lib, monkeypatch):
+    """model shapes stay on chip: the register/shuffle kernel where one warp's lanes cover the rows
+    and a lane can hold its weights (MNIST-sized layers), the shared-memory resident kernel otherwise"""
+    for shape, kind in [((100, 4, 14, 14, 2), "shfl<"), ((100, 8, 7, 7, 2), "shfl<"), ((64, 1, 28, 28, 3), "shfl<"),
+                        ((100, 12, 16, 16, 3), "smem<"), ((100, 24, 8, 8, 3), "smem<"), ((100, 48, 4, 4, 3), "smem<")]:
         B, C, H, W, k = shape
         d = _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1))
-        assert d.startswith("smem<"), (shape, d)
+        assert d.startswith(kind), (shape, d)
+    monkeypatch.setenv("IFK_SOLVE_SHFL", "0")
+    assert _native.describe_solve(_native.problem(100, 4, 14, 14, 2, 2, 4, 1)).startswith("smem<")
+    monkeypatch.delenv("IFK_SOLVE_SHFL")
     big = _native.describe_solve(_native.problem(8, 96, 64, 64, 7, 7, 96, 1))
     assert big.startswith("global")
 

@@ -152,7 +152,7 @@ ORIENT_SHAPES = [(3, 12, 16, 16, 3, 3, 1, 0.02), (2, 8, 7, 7, 2, 2, 4, 0.05), (2
                  (3, 20, 10, 10, 3, 3, 1, 0.02)]
 
 
-@pytest.mark.parametrize("kernel", ["resident", "window", "stream", "global"])
+@pytest.mark.parametrize("kernel", ["default", "resident", "window", "stream", "global"])
 @pytest.mark.parametrize("orient", ["TR", "BL", "BR"])
 @pytest.mark.parametrize("shape", ORIENT_SHAPES, ids=lambda s: "x".join(map(str, s[:7])))
 def test_orientations_by_index_reflection(IF, shape, orient, kernel, monkeypatch):
@@ -165,6 +165,8 @@ def test_orientations_by_index_reflection(IF, shape, orient, kernel, monkeypatch
         monkeypatch.setenv("IFK_SOLVE_STREAM", "1")
     elif kernel == "window":
         monkeypatch.setenv("IFK_SOLVE_WINDOW", "1")
+    elif kernel == "resident":
+        monkeypatch.setenv("IFK_SOLVE_SHFL", "0")       # the shared-memory kernel also where the shuffle kernel applies
     elif kernel == "global":
         monkeypatch.setenv("IFK_SOLVE_GLOBAL", "1")
     B, C, H, W, KH, KW, groups, scale = shape
@@ -173,6 +175,35 @@ def test_orientations_by_index_reflection(IF, shape, orient, kernel, monkeypatch
     g = rng.standard_normal((B, C, H, W)).astype(np.float32)
     w = make_weight(rng, C, C, KH, KW, scale)
     assert_parity(run_all(IF, x, w, g, groups, orient=orient))
+
+
+SHFL_SHAPES = [(100, 4, 14, 14, 2, 2, 1, 0.05), (100, 8, 7, 7, 2, 2, 1, 0.05), (64, 1, 28, 28, 3, 3, 1, 0.1),
+               (9, 4, 14, 14, 3, 3, 1, 0.03), (5, 4, 14, 9, 2, 2, 1, 0.05), (5, 4, 9, 14, 3, 3, 1, 0.03),
+               (7, 8, 7, 7, 2, 2, 4, 0.1), (7, 12, 16, 16, 3, 3, 4, 0.03), (6, 8, 5, 6, 3, 3, 4, 0.02),
+               (3, 2, 32, 5, 2, 2, 1, 0.1), (3, 1, 1, 7, 3, 3, 1, 0.1), (3, 3, 6, 1, 3, 3, 1, 0.1),
+               (1500, 4, 6, 6, 2, 2, 1, 0.05), (4, 3, 10, 12, 3, 3, 1, 0.02), (300, 16, 7, 7, 2, 2, 4, 0.05)]
+
+
+@pytest.mark.parametrize("nct", [0, 1])
+@pytest.mark.parametrize("shape", SHFL_SHAPES, ids=lambda s: "x".join(map(str, s[:7])))
+def test_shuffle_kernel(IF, shape, nct, monkeypatch):
+    """the register/shuffle wavefront kernel (rows on the lanes of one warp, neighbours by warp
+    shuffle), with the widest channel split that fits the warp (default) and with one lane per row"""
+    from inverse_flow_b200 import _native
+    if nct:
+        monkeypatch.setenv("IFK_SHFL_NCT", str(nct))
+    B, C, H, W, KH, KW, groups, scale = shape
+    d = _native.describe_solve(_native.problem(B, C, H, W, KH, KW, C, groups))
+    if nct and not d.startswith("shfl<"):
+        pytest.skip("no one-lane-per-row variant for this group width")
+    assert d.startswith("shfl<"), d
+    rng = np.random.default_rng(23)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, KH, KW, scale)
+    assert_parity(run_all(IF, x, w, g, groups))
+    for orient in ("TR", "BL"):
+        assert_parity(run_all(IF, x[:4], w, g[:4], groups, orient=orient))
 
 
 def test_bad_orient_is_rejected(IF):
