@@ -51,8 +51,14 @@ WORKLOADS = {
 # DRAM bytes (read + write) of ONE launch of the dominant kernel, from a committed ncu --set full
 # capture of that kernel at the workload's stage-1 shape: workload -> (bytes, where it is recorded)
 PROFILED_DRAM_TRAFFIC = {
-    "glow_mnist": (355840, "profiles/r01_ncu_solve_100x4x14.txt (dram__bytes_read 355840 + dram__bytes_write 0)"),
+    "glow_mnist": (326400, "profiles/r01_ncu_shfl_100x4x14.txt (dram__bytes_read 326400 + dram__bytes_write 0)"),
 }
+
+def solve_kernel_name(variant):
+    """__global__ function behind an ifk_describe_solve string"""
+    return {"shfl": "solve_shfl_kernel", "smem": "solve_smem_kernel", "window": "solve_window_kernel",
+            "stream": "solve_stream_kernel"}.get(variant.split("<")[0], "solve_global_kernel")
+
 
 CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -390,7 +396,8 @@ def run_ours(args):
         "traffic": PROFILED_DRAM_TRAFFIC.get(args.workload, (None, None))[0] if args.groups == 1 else None,
         "traffic_source": PROFILED_DRAM_TRAFFIC.get(args.workload, (None, None))[1] if args.groups == 1 else None,
         "peak_source": peak_src,
-        "kernel": "solve_smem_kernel (wavefront triangular solve; inverse and bwd_input)",
+        "kernel": "%s (wavefront triangular solve; inverse and bwd_input)" % solve_kernel_name(
+            _native.describe_solve(st0.problem)),
         "variant": _native.describe_solve(st0.problem),
         "kernel_us": solve_ms * 1e3, "algorithmic_bytes_per_launch": solve_bytes,
         "how": "%d back-to-back launches of ifk_inverse_f32 at stage 1 in a CUDA graph, CUDA events, L2 "

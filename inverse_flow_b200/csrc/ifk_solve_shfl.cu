@@ -198,7 +198,8 @@ solve_shfl_kernel(const ShflParams p)
                     y[i] = active ? acc[i] + late[i] : 0.f;
                     // branch-free: lanes off the image write a scratch word (a divergent branch per
                     // output costs more than the whole FMA chain of a step).  y replaces x in place:
-                    // every lane of this row read x of this pixel one step ago.
+                    // every lane of this row read x of this pixel one step ago.  (Storing y straight to
+                    // HBM from here instead was measured slower: 4.15 vs 3.48 us per kernel.)
                     sts_f32(active ? xa + y_off + ch_stride * i : scratch, y[i]);
                 }
                 // 3. x of the next step's pixel; slide the windows

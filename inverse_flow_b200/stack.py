@@ -17,6 +17,7 @@ End of backward     : one batched stage-2 reduction per stage writes dW of every
                       data-parallel all-reduce consumes.
 """
 import ctypes
+import os
 
 import torch
 
@@ -74,7 +75,12 @@ class InvConvStack:
             st.ws_floats = (ws + 15) // 16 * 4                                        # 16-byte multiple
             st.workspace = torch.empty(n * st.ws_floats, dtype=torch.float32, device=self.device)
             self.stages.append(st)
-        self.side = torch.cuda.Stream(device=self.device)
+        # dW stage 1 of the layers are independent of each other: several side streams let them overlap
+        # (one stream would serialise them and become the critical path once the solves are fast)
+        self.sides = [torch.cuda.Stream(device=self.device) for _ in range(int(os.environ.get("IFK_STACK_SIDE_STREAMS", "8")))]
+        self._side_rr = 0
+        self._sides_forked = []           # side streams forked since the last join (a graph capture must
+                                          # only join streams that are part of it)
         self.graph = None
         # per stage: 1 prepare + n inverse + n dX + n dW stage 1 + 1 dW stage 2
         self.launches_per_step = sum(3 * st.n + 2 for st in self.stages)
@@ -93,27 +99,32 @@ class InvConvStack:
                                               st.act[i + 1].data_ptr(), s))
 
     def backward_stage(self, st):
-        """dX chain on the current stream, dW stage 1 of every layer forked onto the side stream."""
+        """dX chain on the current stream, dW stage 1 of every layer forked onto a side stream."""
         lib = self.lib
         main = torch.cuda.current_stream(self.device)
         s = ctypes.c_void_p(main.cuda_stream)
-        side_s = ctypes.c_void_p(self.side.cuda_stream)
         p = ctypes.byref(st.problem)
         g = st.grad_in
         for i in reversed(range(st.n)):
             dx = st.dxs[i]
             _native.check(lib.ifk_bwd_input_f32(p, g.data_ptr(), st.prepared[i].data_ptr(), dx.data_ptr(), s))
-            self.side.wait_stream(main)                       # fork: dW stage 1 needs this dX
+            side = self.sides[self._side_rr % len(self.sides)]
+            self._side_rr += 1
+            side.wait_stream(main)                            # fork: dW stage 1 needs this dX
+            if side not in self._sides_forked:
+                self._sides_forked.append(side)
             ws = st.workspace[i * st.ws_floats:]
             _native.check(lib.ifk_bwd_weight_partial_f32(p, dx.data_ptr(), st.act[i + 1].data_ptr(),
-                                                         ws.data_ptr(), side_s))
+                                                         ws.data_ptr(), ctypes.c_void_p(side.cuda_stream)))
             g = dx
         st.dx = g
 
     def finish_weight_gradients(self, stages=None):
-        """join the side stream, then one batched dW stage 2 per stage into the flat bucket."""
+        """join the side streams, then one batched dW stage 2 per stage into the flat bucket."""
         main = torch.cuda.current_stream(self.device)
-        main.wait_stream(self.side)
+        for side in self._sides_forked:
+            main.wait_stream(side)
+        self._sides_forked = []
         s = ctypes.c_void_p(main.cuda_stream)
         for st in (self.stages if stages is None else stages):
             _native.check(self.lib.ifk_bwd_weight_reduce_many_f32(
