@@ -129,6 +129,44 @@ __device__ __forceinline__ void lds_vec<4>(float *v, uint32_t addr)
                  : "memory");
 }
 
+// ---- packed FP32: two FMAs per instruction (SASS FFMA2) ---------------------------------------
+// A three-register FFMA issues every other cycle per scheduler on this architecture; the packed form
+// does two per instruction, so FMA-bound inner loops need half the issue slots.  The pairs run along
+// the REDUCTION axis -- (w[i], w[i+1]) * (v[i], v[i+1]) accumulate into (lo, hi) halves that are added
+// at the end -- so loaded values pair up as they arrive (ld.shared.v2.b64) and nothing is duplicated.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float sum_f32x2(f32x2_t v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+__device__ __forceinline__ f32x2_t fma_f32x2(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// VEC floats from shared memory as VEC/2 packed pairs
+template <int VEC>
+__device__ __forceinline__ void lds_pairs(f32x2_t *v, uint32_t addr);
+template <>
+__device__ __forceinline__ void lds_pairs<2>(f32x2_t *v, uint32_t addr)
+{
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[0]) : "r"(addr) : "memory");
+}
+template <>
+__device__ __forceinline__ void lds_pairs<4>(f32x2_t *v, uint32_t addr)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(addr) : "memory");
+}
+
 // ---- reduce-scatter of N partial sums over the NS adjacent lanes of a pixel ------------------
 // Recursive halving: at the level with lane mask m every lane keeps one half of its current
 // values and receives the partner's partial sums of that half (N/2 + N/4 + ... shuffles in
@@ -287,6 +325,15 @@ solve_smem_kernel(const SolveParams p)
         }
     }
 
+    // the same weights as packed pairs along the reduction axis (the scalar array is dead afterwards)
+    f32x2_t w2[CC][(NV * VEC + 1) / 2];
+    if constexpr (VEC >= 2) {
+#pragma unroll
+        for (int cc = 0; cc < CC; cc++)
+#pragma unroll
+            for (int i = 0; i < NV * VEC / 2; i++) w2[cc][i] = pack_f32x2(wreg[cc][2 * i], wreg[cc][2 * i + 1]);
+    }
+
     if (Cg > 1)
         for (int i = tid; i < Cg * p.CgP4; i += nthr) {
             const int ci = i / p.CgP4, co = i - ci * p.CgP4;
@@ -385,6 +432,27 @@ solve_smem_kernel(const SolveParams p)
         IFK_PROBE(5);
         auto step = [&](uint32_t pix, uint32_t za, bool active) {
             const uint32_t pa = active ? pix : ybase;              // idle lanes: a legal pixel
+            if constexpr (VEC >= 2) {
+                // packed path: values arrive as pairs, two FMAs per instruction
+                f32x2_t v2[NV * VEC / 2];
+#pragma unroll
+                for (int j = 0; j < NV; j++) lds_pairs<VEC>(v2 + j * (VEC / 2), pa + (uint32_t)offs[j]);
+                float zv[CC];
+#pragma unroll
+                for (int i = 0; i < CC; i++) zv[i] = (active && i < own_size) ? lds_f32(za + zstride * i) : 0.f;
+                f32x2_t acc2[CC];
+#pragma unroll
+                for (int cc = 0; cc < CC; cc++) acc2[cc] = 0ull;
+#pragma unroll
+                for (int i = 0; i < NV * VEC / 2; i++)
+#pragma unroll
+                    for (int cc = 0; cc < CC; cc++) acc2[cc] = fma_f32x2(w2[cc][i], v2[i], acc2[cc]);
+                float acc[CC];
+#pragma unroll
+                for (int cc = 0; cc < CC; cc++) acc[cc] = sum_f32x2(acc2[cc]);
+                Rs<CC, 5>::run(acc, zv, ks, NSr, own_size, active, pa + own_c0_bytes, za, zstride);
+                return;
+            }
             float v[NV * VEC];
 #pragma unroll
             for (int j = 0; j < NV; j++) lds_vec<VEC>(v + j * VEC, pa + (uint32_t)offs[j]);
