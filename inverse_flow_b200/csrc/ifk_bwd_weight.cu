@@ -78,6 +78,8 @@ struct BwdWeightParams {
     const float *dx, *y;
     float *partial;
     int B, C, H, W, KH, KW, Cg, ntk, items, per_chunk, nbuf, nstage, XN, bulk, orient;
+    unsigned w_magic;   // ceil(2^32 / W): r / W == umulhi(r, w_magic) while r * W < 2^32 (staged images are far
+                        // smaller); 0 when W == 1
 };
 
 // sum N per-lane values over the 32 lanes by recursive halving: N/2 + N/4 + ... shuffles
@@ -126,6 +128,10 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
     const int aoff = c0 * HW, voff = k0 * HW - ((fh ? -qh : qh) * W + (fw ? -qw : qw));
     const int h_lo = fh ? 0 : qh, h_hi = fh ? p.H - 1 - qh : p.H - 1;     // rows / columns whose neighbour exists
     const int w_lo = fw ? 0 : qw, w_hi = fw ? W - 1 - qw : W - 1;
+    // a tap that reaches outside the image from every pixel (kernel larger than the image) sums nothing;
+    // otherwise `neutral_r` is a pixel whose neighbour exists: the load address of lanes that contribute zero
+    const bool empty = h_lo > h_hi || w_lo > w_hi;
+    const int neutral_r = empty ? 0 : h_lo * W + w_lo;
     float acc[TC * TK];
 #pragma unroll
     for (int i = 0; i < TC * TK; i++) acc[i] = 0.f;
@@ -155,7 +161,7 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
         const int n0 = b_end - b_begin < nstage ? b_end - b_begin : nstage;
         issue(0, b_begin, n0);
     }
-    if (staged) {       // channels padded up to the tile are zero for good (bulk copies never touch them)
+    if (staged && XN > Cg * HW) {   // channels padded up to the tile are zero for good (bulk copies never touch them)
         for (int bsel = 0; bsel < 2 * p.nbuf * nstage; bsel++)
             for (int i = Cg * HW + tid; i < XN; i += blockDim.x) buf0[(size_t)bsel * XN + i] = 0.f;
     }
@@ -191,9 +197,33 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
             stage_base = nullptr;
         }
 
-        if (live) {
-            // lanes stride over the (image, pixel) pairs of the stage: every shared-memory read is
-            // 32 consecutive words, and tiny images still fill the warp
+        if (live && staged && !empty) {
+            // lanes stride over the (image, pixel) pairs of the stage: every shared-memory read is 32
+            // consecutive words, and tiny images still fill the warp.  The walk advances (image, pixel)
+            // by 32 pairs with one conditional subtraction; row / column come from one multiply-high;
+            // pixels whose neighbour lies outside the image multiply by zero instead of branching
+            // (a divergent branch around the tile costs more than its FMAs at these sizes).
+            int im = lane / HW, r = lane - im * HW;          // once per stage
+            const int d_im = 32 / HW, d_r = 32 - d_im * HW;
+            while (im < n_img) {
+                const int h = p.w_magic ? (int)__umulhi((unsigned)r, p.w_magic) : r, w = r - h * W;   // W == 1: h = r
+                const bool ok = h >= h_lo && h <= h_hi && w >= w_lo && w <= w_hi;
+                const float *dxs = stage_base + (size_t)(2 * im) * XN, *ys = dxs + XN;
+                const int rv = ok ? r : neutral_r;           // a pixel whose neighbour exists (address safety)
+                float a[TC], v[TK];
+#pragma unroll
+                for (int i = 0; i < TC; i++) a[i] = ok ? dxs[aoff + i * HW + r] : 0.f;
+#pragma unroll
+                for (int k = 0; k < TK; k++) v[k] = ys[voff + k * HW + rv];
+#pragma unroll
+                for (int i = 0; i < TC; i++)
+#pragma unroll
+                    for (int k = 0; k < TK; k++) acc[i * TK + k] = fmaf(a[i], v[k], acc[i * TK + k]);
+                r += d_r;
+                im += d_im;
+                if (r >= HW) { r -= HW; im++; }
+            }
+        } else if (live && !staged) {
             int im = 0, h = 0, w = lane;
             while (w >= W) { w -= W; h++; }
             while (h >= p.H) { h -= p.H; im++; }
@@ -201,21 +231,13 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
                 if (h >= h_lo && h <= h_hi && w >= w_lo && w <= w_hi) {
                     const int r = h * W + w;
                     float a[TC], v[TK];
-                    if (staged) {
-                        const float *dxs = stage_base + (size_t)(2 * im) * XN, *ys = dxs + XN;
+                    const float *dxs = dx0 + (size_t)(b + im) * img_stride, *ys = y0 + (size_t)(b + im) * img_stride;
 #pragma unroll
-                        for (int i = 0; i < TC; i++) a[i] = dxs[aoff + i * HW + r];
+                    for (int i = 0; i < TC; i++)
+                        a[i] = c0 + i < Cg ? __ldg(dxs + aoff + i * HW + r) : 0.f;
 #pragma unroll
-                        for (int k = 0; k < TK; k++) v[k] = ys[voff + k * HW + r];
-                    } else {
-                        const float *dxs = dx0 + (size_t)(b + im) * img_stride, *ys = y0 + (size_t)(b + im) * img_stride;
-#pragma unroll
-                        for (int i = 0; i < TC; i++)
-                            a[i] = c0 + i < Cg ? __ldg(dxs + aoff + i * HW + r) : 0.f;
-#pragma unroll
-                        for (int k = 0; k < TK; k++)
-                            v[k] = k0 + k < Cg ? __ldg(ys + voff + k * HW + r) : 0.f;
-                    }
+                    for (int k = 0; k < TK; k++)
+                        v[k] = k0 + k < Cg ? __ldg(ys + voff + k * HW + r) : 0.f;
 #pragma unroll
                     for (int i = 0; i < TC; i++)
 #pragma unroll
@@ -320,6 +342,7 @@ int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y
     p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW; p.Cg = g.Cg;
     p.ntk = pl.ntk; p.items = pl.items; p.per_chunk = pl.per_chunk;
     p.nbuf = pl.nbuf; p.nstage = pl.nstage; p.XN = pl.XN; p.orient = g.orient;
+    p.w_magic = g.W > 1 ? (unsigned)((0x100000000ULL + g.W - 1) / g.W) : 0u;      // 0: single column
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) ? 1 : 0;
     if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
