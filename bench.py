@@ -60,6 +60,50 @@ def solve_kernel_name(variant):
             "stream": "solve_stream_kernel"}.get(variant.split("<")[0], "solve_global_kernel")
 
 
+def wavefront_step_accounting(lib, p0, st0, device):
+    """The latency roofline of the solve: cycles one anti-diagonal costs inside the kernel's loop
+    (clock64 stamps of CTA 0 around the loop, one extra probed launch) against the dependent chain
+    of one step built from measured instruction latencies (B300_MICROARCH.md: ld.shared 29, FMA 4,
+    named barrier ~47; warp shuffle ~24)."""
+    import ctypes
+    import re
+    import torch
+    from inverse_flow_b200 import _native
+    lib.ifk_debug_set_probe.argtypes = [ctypes.c_void_p]
+    lib.ifk_debug_set_probe.restype = None
+    probe = torch.zeros(16, dtype=torch.int64, device=device)
+    lib.ifk_debug_set_probe(ctypes.c_void_p(probe.data_ptr()))
+    try:
+        _native.check(lib.ifk_inverse_f32(p0, st0.act[0].data_ptr(), st0.prepared[0].data_ptr(),
+                                          st0.act[1].data_ptr(), _native.current_stream(device)))
+        torch.cuda.synchronize()
+    finally:
+        lib.ifk_debug_set_probe(None)
+    t = probe.cpu().tolist()
+    steps = st0.H + st0.W - 1
+    variant = _native.describe_solve(st0.problem)
+    if t[6] <= t[5] or t[8] <= t[0]:
+        return {"steps": steps, "note": "this kernel variant carries no probe stamps"}
+    loop = (t[6] - t[5]) / steps
+    Cg = st0.C // st0.groups
+    if variant.startswith("shfl"):
+        chain = 24 + 4 + 4 * Cg + 4 + 4
+        what = "shuffle 24 + select 4 + %d dependent FMAs (the taps fed by the fresh values) + add 4 + select 4" % Cg
+    else:
+        m = re.search(r"cc=(\d+),nv=(\d+),vec=(\d+)> ns=(\d+)", variant)
+        cc, nv, vec, ns = (int(v) for v in m.groups()) if m else (1, 1, 1, 1)
+        nacc = 2 if vec >= 2 else (1 if cc >= 4 else (2 if cc >= 2 else 4))
+        levels = max(ns.bit_length() - 1, 0)
+        multi = "threads=128(32)" not in variant
+        chain = 29 + 4 * (nv * vec // nacc) + 24 * levels + 8 + (47 if multi else 10)
+        what = ("ld.shared 29 + %d-deep FMA chain + %d shuffle levels x 24 + adds 8 + %s" %
+                (nv * vec // nacc, levels, "named barrier 47" if multi else "syncwarp 10"))
+    return {"steps": steps, "loop_cycles_per_step": loop, "floor_cycles_per_step": chain, "frac": chain / loop,
+            "loop_share_of_kernel": (t[6] - t[5]) / (t[8] - t[0]), "kernel_cycles": t[8] - t[0],
+            "floor": what,
+            "how": "clock64 stamps of CTA 0 around the diagonal loop (ifk_debug_set_probe), one probed launch"}
+
+
 CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
                "clocks_event_reasons.sw_power_cap")
@@ -408,6 +452,8 @@ def run_ours(args):
         "note": "latency-bound at model shapes: the image (%.0f KB) moves in well under a microsecond; the "
                 "binding term is the (H+W-1)-step dependency chain (see DESIGN.md roofline)" % (solve_bytes / 1e3),
     }
+
+    roofline["wavefront"] = wavefront_step_accounting(lib, p0, st0, device)
 
     line = base_line(args, stages, batch, desc, n_gpus)
     line.update({

@@ -144,6 +144,13 @@ int ifk_backward_f32(const ifk_problem *p, const float *g, const float *y,
  * e.g. "smem<cc=4,nv=6,vec=4> ns=4 nct=3 slots=16 iters=1 threads=192(192) ..." or "global ...". */
 int ifk_describe_solve(const ifk_problem *p, char *buf, size_t buflen);
 
+/* Phase timing of the resident and shuffle solve kernels: while `device_buffer` (16 x int64 of
+ * device memory) is set, thread 0 of CTA (0,0) of every such solve writes clock64() stamps into
+ * it -- 0 kernel start, 1..3 prologue done, 4 image landed, 5 / 6 diagonal loop start / end,
+ * 7 store issued, 8 end.  NULL switches it off (the default).  Process-wide; a measuring aid
+ * for bench.py's wavefront accounting and tools/probe_solve.py, not for concurrent use. */
+void ifk_debug_set_probe(long long *device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ EXPORTS = (
     "ifk_version", "ifk_status_string", "ifk_prepared_floats", "ifk_prepare_f32", "ifk_prepare_many_f32",
     "ifk_inverse_f32", "ifk_conv_f32", "ifk_bwd_input_f32", "ifk_bwd_weight_workspace_bytes",
     "ifk_bwd_weight_f32", "ifk_bwd_weight_partial_f32", "ifk_bwd_weight_reduce_many_f32",
-    "ifk_backward_f32", "ifk_describe_solve",
+    "ifk_backward_f32", "ifk_describe_solve", "ifk_debug_set_probe",
 )
 
 

@@ -157,7 +157,7 @@ int ifk_backward_f32(const ifk_problem *p, const float *grad, const float *y, co
     return ifk_bwd_weight_f32(p, dx, y, dw, workspace, stream);
 }
 
-// Tuning aid, deliberately not in ifk.h: device buffer of >= 16 int64 that CTA (0,0) of the
+// Measuring aid (ifk.h, "introspection"): device buffer of >= 16 int64 that CTA (0,0) of the
 // next solve launches fills with clock64() stamps of its phases (nullptr switches it off).
 void ifk_debug_set_probe(long long *device_buffer) { set_solve_probe(device_buffer); }
 

@@ -52,6 +52,7 @@ int describe_shfl_solve(const Geometry &g, char *buf, size_t buflen);
 int launch_solve_shfl(const Geometry &g, const float *in, const float *prep_dir, float *out, bool reverse,
                       cudaStream_t s);
 void set_solve_probe(long long *device_buffer);
+long long *get_solve_probe();
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 

@@ -221,6 +221,7 @@ static int large_image_kernel(const Geometry &g)
 
 static long long *g_probe = nullptr;   // tuning aid, see ifk_debug_set_probe
 void set_solve_probe(long long *p) { g_probe = p; }
+long long *get_solve_probe() { return g_probe; }
 
 int launch_solve(const Geometry &g, const float *in, const float *prep_dir, float *out,
                  bool reverse, cudaStream_t s)

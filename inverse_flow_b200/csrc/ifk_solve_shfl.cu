@@ -38,6 +38,26 @@ struct ShflParams {
     int B, C, H, W, KDP, CgP4, XN;
     int flip;           // as SolveParams::flip
     int bulk;
+    long long *probe;   // tuning aid: clock64() stamps of CTA (0,0) lane 0 (same slots as the resident kernel)
+};
+
+// One "element" of the input-channel axis: a packed pair of channels (two FMAs per instruction, SASS
+// FFMA2) when the group width is even, a single float otherwise.  A lone warp issues in order and a
+// three-register FFMA occupies the FMA pipe for two cycles, so halving the FMA count shortens the step.
+template <int P> struct ShflElem;
+template <> struct ShflElem<1> {
+    typedef float type;
+    __device__ __forceinline__ static float zero() { return 0.f; }
+    __device__ __forceinline__ static float make(const float *v) { return v[0]; }
+    __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    __device__ __forceinline__ static float sum(float v) { return v; }
+};
+template <> struct ShflElem<2> {
+    typedef f32x2_t type;
+    __device__ __forceinline__ static f32x2_t zero() { return 0ull; }
+    __device__ __forceinline__ static f32x2_t make(const float *v) { return pack_f32x2(v[0], v[1]); }
+    __device__ __forceinline__ static f32x2_t fma(f32x2_t a, f32x2_t b, f32x2_t c) { return fma_f32x2(a, b, c); }
+    __device__ __forceinline__ static float sum(f32x2_t v) { return sum_f32x2(v); }
 };
 
 template <int CG, int NCT, int KH, int KW>
@@ -47,7 +67,14 @@ solve_shfl_kernel(const ShflParams p)
     constexpr int CC = CG / NCT;            // output channels per lane
     constexpr int K = KH * KW;
     constexpr int KW1 = KW > 1 ? KW - 1 : 1;
+    // Packed pairs (P = 2) were measured SLOWER here than scalar FMAs (174 vs 152 cycles per diagonal at
+    // (100,4,14,14) k=2): the pack moves and the longer FFMA2 latency sit on the one warp's dependent chain.
+    constexpr int P = 1;                                // input channels per element
+    constexpr int CE = CG / P;                          // elements per pixel
+    typedef ShflElem<P> E;
+    typedef typename E::type elem_t;
     static_assert(CG % NCT == 0, "channel tiles must divide the group");
+    IFK_PROBE(0);
     extern __shared__ __align__(128) float smem[];
     const int H = p.H, W = p.W, HW = p.H * p.W;
     const int lane = threadIdx.x;
@@ -68,17 +95,27 @@ solve_shfl_kernel(const ShflParams p)
 
     const int row = lane / NCT, ct = lane - row * NCT;
     const bool valid = row < H;
-    float wreg[CC][K > 1 ? K - 1 : 1][CG];
-    float treg[CC][CG];                     // rows of T = (I + A0)^-1: z = T x is formed on the fly
+    elem_t wreg[CC][K > 1 ? K - 1 : 1][CE];
+    elem_t treg[CC][CE];                    // rows of T = (I + A0)^-1: z = T x is formed on the fly
 #pragma unroll
     for (int i = 0; i < CC; i++) {
+        const float *wrow = wg + (size_t)(ct * CC + i) * p.KDP;
 #pragma unroll
         for (int t = 1; t < K; t++)
 #pragma unroll
-            for (int ci = 0; ci < CG; ci++)
-                wreg[i][t - 1][ci] = __ldg(wg + (size_t)(ct * CC + i) * p.KDP + t * CG + ci);
+            for (int e = 0; e < CE; e++) {
+                float tmp[P];
 #pragma unroll
-        for (int ci = 0; ci < CG; ci++) treg[i][ci] = __ldg(wg + (size_t)(ct * CC + i) * p.KDP + ci);
+                for (int q = 0; q < P; q++) tmp[q] = __ldg(wrow + t * CG + e * P + q);
+                wreg[i][t - 1][e] = E::make(tmp);
+            }
+#pragma unroll
+        for (int e = 0; e < CE; e++) {
+            float tmp[P];
+#pragma unroll
+            for (int q = 0; q < P; q++) tmp[q] = __ldg(wrow + e * P + q);
+            treg[i][e] = E::make(tmp);
+        }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int b = blockIdx.x;
@@ -90,6 +127,9 @@ solve_shfl_kernel(const ShflParams p)
         }
     }
     __syncwarp();
+    IFK_PROBE(1);       // weights and T in registers, previous kernel finished (griddepcontrol.wait), load issued
+    IFK_PROBE(2);
+    IFK_PROBE(3);
 
     // memory index of solver pixel (h, w) = idx0 + sh*h*W + sw*w (reflected axes walk backwards)
     const int sw = (p.flip & 1) ? -1 : 1, sh = (p.flip & 2) ? -1 : 1;
@@ -113,17 +153,19 @@ solve_shfl_kernel(const ShflParams p)
             for (int i = lane; i < CG * HW; i += 32) xbuf[i] = __ldg(src + i);
             __syncwarp();
         }
+        IFK_PROBE(4);   // image landed
+        IFK_PROBE(5);
 
         {
             // win[qh][j] = y(h - qh, w - 1 - j): what this step needs at column offset j + 1
-            float win[KH][KW1][CG];
+            elem_t win[KH][KW1][CE];
             float hist[KH > 1 ? KH - 1 : 1][CC];    // this lane's outputs 2, 3, .. steps ago
 #pragma unroll
             for (int qh = 0; qh < KH; qh++)
 #pragma unroll
                 for (int j = 0; j < KW1; j++)
 #pragma unroll
-                    for (int c = 0; c < CG; c++) win[qh][j][c] = 0.f;
+                    for (int c = 0; c < CE; c++) win[qh][j][c] = E::zero();
 #pragma unroll
             for (int s = 0; s < (KH > 1 ? KH - 1 : 1); s++)
 #pragma unroll
@@ -140,6 +182,11 @@ solve_shfl_kernel(const ShflParams p)
 
             for (int d = 0; d < ndiag; d++, col++, xa += x_step) {
                 const bool active = valid && (unsigned)col < (unsigned)W;
+                // 0. x of the NEXT step's pixel: issued first, so that the loads have the whole step to land
+                const bool next_active = valid && (unsigned)(col + 1) < (unsigned)W;
+                float xnext[CG];
+#pragma unroll
+                for (int c = 0; c < CG; c++) xnext[c] = next_active ? lds_f32(xa + x_step + ch_stride * c) : 0.f;
                 // 1. the newest neighbours, straight from the producing lanes' registers
                 float fresh[KH][CG];                // fresh[qh] = y(h - qh, w) for qh >= 1; fresh[0] = y(h, w - 1)
 #pragma unroll
@@ -163,49 +210,55 @@ solve_shfl_kernel(const ShflParams p)
                         }
 
                 // 2. while the shuffles are in flight: z = T x of this pixel and the older columns
-                float acc[CC], late[CC];
+                elem_t acc[CC], late[CC], xe[CE];
+#pragma unroll
+                for (int e = 0; e < CE; e++) xe[e] = E::make(xv + e * P);
 #pragma unroll
                 for (int i = 0; i < CC; i++) {
-                    acc[i] = 0.f;
-                    late[i] = 0.f;
+                    acc[i] = E::zero();
+                    late[i] = E::zero();
                 }
 #pragma unroll
-                for (int ci = 0; ci < CG; ci++)
+                for (int e = 0; e < CE; e++)
 #pragma unroll
-                    for (int i = 0; i < CC; i++) late[i] = fmaf(treg[i][ci], xv[ci], late[i]);
+                    for (int i = 0; i < CC; i++) late[i] = E::fma(treg[i][e], xe[e], late[i]);
 #pragma unroll
                 for (int qh = 0; qh < KH; qh++)
 #pragma unroll
                     for (int qw = (qh == 0 ? 2 : 1); qw < KW; qw++)
 #pragma unroll
-                        for (int ci = 0; ci < CG; ci++)
+                        for (int e = 0; e < CE; e++)
 #pragma unroll
                             for (int i = 0; i < CC; i++)
-                                acc[i] = fmaf(wreg[i][qh * KW + qw - 1][ci], win[qh][qw - 1][ci], acc[i]);
+                                acc[i] = E::fma(wreg[i][qh * KW + qw - 1][e], win[qh][qw - 1][e], acc[i]);
                 //    then the fresh values: tap (0, 1) on one chain, taps (qh, 0) on the other
+                elem_t fe[KH][CE];
 #pragma unroll
-                for (int ci = 0; ci < CG; ci++)
+                for (int qh = 0; qh < KH; qh++)
+#pragma unroll
+                    for (int e = 0; e < CE; e++) fe[qh][e] = E::make(fresh[qh] + e * P);
+#pragma unroll
+                for (int e = 0; e < CE; e++)
 #pragma unroll
                     for (int i = 0; i < CC; i++) {
-                        if (KW > 1) late[i] = fmaf(wreg[i][0][ci], fresh[0][ci], late[i]);
+                        if (KW > 1) late[i] = E::fma(wreg[i][0][e], fe[0][e], late[i]);
 #pragma unroll
                         for (int qh = 1; qh < KH; qh++)
-                            acc[i] = fmaf(wreg[i][qh * KW - 1][ci], fresh[qh][ci], acc[i]);
+                            acc[i] = E::fma(wreg[i][qh * KW - 1][e], fe[qh][e], acc[i]);
                     }
                 float y[CC];
 #pragma unroll
                 for (int i = 0; i < CC; i++) {
-                    y[i] = active ? acc[i] + late[i] : 0.f;
+                    y[i] = active ? E::sum(acc[i]) + E::sum(late[i]) : 0.f;
                     // branch-free: lanes off the image write a scratch word (a divergent branch per
                     // output costs more than the whole FMA chain of a step).  y replaces x in place:
                     // every lane of this row read x of this pixel one step ago.  (Storing y straight to
                     // HBM from here instead was measured slower: 4.15 vs 3.48 us per kernel.)
                     sts_f32(active ? xa + y_off + ch_stride * i : scratch, y[i]);
                 }
-                // 3. x of the next step's pixel; slide the windows
-                const bool next_active = valid && (unsigned)(col + 1) < (unsigned)W;
+                // 3. slide the windows
 #pragma unroll
-                for (int c = 0; c < CG; c++) xv[c] = next_active ? lds_f32(xa + x_step + ch_stride * c) : 0.f;
+                for (int c = 0; c < CG; c++) xv[c] = xnext[c];
                 // windows for the next step (column w + 1): win'[qh][j] = y(h - qh, w - j).  Row 0 lags:
                 // y(h, w) of this step reaches the sibling lanes by next step's shuffle (fresh[0]), so
                 // win[0][0] is never read and win'[0][1] = y(h, w - 1) = this step's fresh[0].
@@ -214,17 +267,17 @@ solve_shfl_kernel(const ShflParams p)
 #pragma unroll
                     for (int j = KW1 - 1; j >= 1; j--)
 #pragma unroll
-                        for (int c = 0; c < CG; c++) win[qh][j][c] = win[qh][j - 1][c];
+                        for (int c = 0; c < CE; c++) win[qh][j][c] = win[qh][j - 1][c];
 #pragma unroll
-                    for (int c = 0; c < CG; c++) win[qh][0][c] = fresh[qh][c];
+                    for (int c = 0; c < CE; c++) win[qh][0][c] = fe[qh][c];
                 }
 #pragma unroll
                 for (int j = KW1 - 1; j >= 2; j--)
 #pragma unroll
-                    for (int c = 0; c < CG; c++) win[0][j][c] = win[0][j - 1][c];
+                    for (int c = 0; c < CE; c++) win[0][j][c] = win[0][j - 1][c];
                 if (KW1 > 1) {
 #pragma unroll
-                    for (int c = 0; c < CG; c++) win[0][1][c] = fresh[0][c];
+                    for (int c = 0; c < CE; c++) win[0][1][c] = fe[0][c];
                 }
 #pragma unroll
                 for (int s = (KH > 1 ? KH - 2 : 0); s >= 1; s--)
@@ -239,6 +292,7 @@ solve_shfl_kernel(const ShflParams p)
             }
         }
 
+        IFK_PROBE(6);   // diagonal loop done
         float *dst = out0 + (size_t)b * img_stride;
         if (p.bulk) {
             fence_async_proxy();            // generic-proxy writes of xbuf -> visible to the TMA engine
@@ -257,7 +311,9 @@ solve_shfl_kernel(const ShflParams p)
             __syncwarp();
         }
     }
+    IFK_PROBE(7);
     if (p.bulk && lane == 0) bulk_store_wait_read();   // smem must outlive the last store's read
+    IFK_PROBE(8);
 }
 
 // ---- host side -----------------------------------------------------------------------------
@@ -333,6 +389,7 @@ int launch_solve_shfl(const Geometry &g, const float *in, const float *prep_dir,
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0) ? 1 : 0;
     if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
+    p.probe = get_solve_probe();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c.grid_x, g.groups);
     cfg.blockDim = dim3(32);
