@@ -51,7 +51,7 @@ WORKLOADS = {
 # DRAM bytes (read + write) of ONE launch of the dominant kernel, from a committed ncu --set full
 # capture of that kernel at the workload's stage-1 shape: workload -> (bytes, where it is recorded)
 PROFILED_DRAM_TRAFFIC = {
-    "glow_mnist": (326400, "profiles/r01_ncu_shfl_100x4x14.txt (dram__bytes_read 326400 + dram__bytes_write 0)"),
+    "glow_mnist": (327168, "profiles/r01_ncu_shfl_100x4x14.txt (dram__bytes_read 327168 + dram__bytes_write 0)"),
 }
 
 def solve_kernel_name(variant):
