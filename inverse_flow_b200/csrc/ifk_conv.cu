@@ -9,8 +9,11 @@
 // output channels) items: per (tap, ci) one coalesced global load of y (neighbouring pixels
 // overlap in L1) and one broadcast 128-bit shared load of 4 weights feed 4 FMAs; the border
 // test is per tap, not per element.
-// conv_kernel: one thread per output, everything through L1/L2 -- used for single-channel and
-// for wide groups (Cg > 16), where staging the weights per CTA costs more than it saves.
+// conv_wide_kernel: wide groups (Cg > 16) whose staged weights fit shared memory: 4 pixels x 4 output
+// channels per thread with a sliding row window (see the kernel).
+// conv_kernel: one thread per output, everything through L1/L2 -- single-channel groups and whatever the
+// staged kernels cannot hold.
+#include <stdlib.h>
 #include "ifk_internal.cuh"
 
 namespace ifk {
@@ -75,6 +78,93 @@ conv_tiled_kernel(const float *__restrict__ y, const float *__restrict__ weight,
     }
 }
 
+// conv_wide_kernel: wide groups (Cg > 16).  Same staged weights as conv_tiled_kernel; a thread owns a
+// 4-pixel run of one image row x 4 output channels and, per (row offset qh, input channel), loads the
+// KW + 3 values y(h - qh, w0 - KW + 1 .. w0 + 3) once and slides them over the KW taps: KW 128-bit
+// weight loads and KW + 3 cached global loads feed 16 * KW FMAs (the one-output-per-thread kernel does one
+// load per FMA).  Coordinates are the causal frame's; the reflection of an orientation is applied where
+// memory is touched.
+template <int KWT>
+__global__ void __launch_bounds__(256)
+conv_wide_kernel(const float *__restrict__ y, const float *__restrict__ weight, float *__restrict__ x,
+                 int B, int C, int H, int W, int KH, int Cw, int Cg, int CgP4, int nsplit, int orient)
+{
+    constexpr int KW = KWT;
+    extern __shared__ __align__(16) float wT[];              // [K][Cg][CgP4]
+    const int HW = H * W, K = KH * KW;
+    const int G = blockIdx.y, tid = threadIdx.x;
+    const size_t tap_stride = (size_t)K, row_stride = (size_t)Cw * tap_stride;
+    const float *wg = weight + (size_t)G * Cg * row_stride;
+    for (int e = tid; e < K * Cg * CgP4; e += blockDim.x) {
+        const int co = e % CgP4, ci = (e / CgP4) % Cg, t = e / (CgP4 * Cg);
+        const int qh = t / KW, qw = t - qh * KW;
+        const int a = (KH - 1 - qh) * KW + (KW - 1 - qw);
+        float v = 0.f;
+        if (co < Cg) {
+            if (t == 0) v = ci < co ? __ldg(wg + co * row_stride + ci * tap_stride + a) : (ci == co ? 1.f : 0.f);
+            else        v = __ldg(wg + co * row_stride + ci * tap_stride + a);
+        }
+        wT[e] = v;
+    }
+    __syncthreads();
+
+    const bool fw = orient & 1, fh = orient & 2;
+    const int nquad = CgP4 >> 2, wq = (W + 3) >> 2;
+    const int items = H * wq * nquad;
+    for (int u = blockIdx.x; u < B * nsplit; u += gridDim.x) {
+        const int b = u / nsplit, sp = u - b * nsplit;
+        const float *yb = y + ((size_t)b * C + (size_t)G * Cg) * HW;
+        float *xb = x + ((size_t)b * C + (size_t)G * Cg) * HW;
+        for (int item = sp * blockDim.x + tid; item < items; item += nsplit * blockDim.x) {
+            // consecutive threads -> consecutive pixel runs of one output quad (coalesced y, broadcast weights)
+            const int cq = item / (H * wq), r = item - cq * (H * wq);
+            const int h = r / wq, w0 = (r - h * wq) * 4;
+            float acc[4][4];
+#pragma unroll
+            for (int px = 0; px < 4; px++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[px][j] = 0.f;
+            const int qh_max = h < KH - 1 ? h : KH - 1;
+            for (int qh = 0; qh <= qh_max; qh++) {
+                const int hn = h - qh, hm = fh ? H - 1 - hn : hn;
+                const float *yrow = yb + hm * W;
+                const float *wrow = wT + (size_t)(qh * KW) * Cg * CgP4 + cq * 4;
+                for (int ci = 0; ci < Cg; ci++) {
+                    float yv[KW + 3];                         // y(hn, w0 - KW + 1 + j)
+#pragma unroll
+                    for (int j = 0; j < KW + 3; j++) {
+                        const int w = w0 - (KW - 1) + j;
+                        yv[j] = (w >= 0 && w < W) ? __ldg(yrow + (size_t)ci * HW + (fw ? W - 1 - w : w)) : 0.f;
+                    }
+#pragma unroll
+                    for (int qw = 0; qw < KW; qw++) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(wrow + ((size_t)qw * Cg + ci) * CgP4);
+#pragma unroll
+                        for (int px = 0; px < 4; px++) {
+                            const float v = yv[px + (KW - 1) - qw];
+                            acc[px][0] = fmaf(w4.x, v, acc[px][0]);
+                            acc[px][1] = fmaf(w4.y, v, acc[px][1]);
+                            acc[px][2] = fmaf(w4.z, v, acc[px][2]);
+                            acc[px][3] = fmaf(w4.w, v, acc[px][3]);
+                        }
+                    }
+                }
+            }
+            const int co = cq * 4, hmo = fh ? H - 1 - h : h;
+#pragma unroll
+            for (int px = 0; px < 4; px++) {
+                const int w = w0 + px;
+                if (w < W) {
+                    float *xp = xb + hmo * W + (fw ? W - 1 - w : w);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (co + j < Cg) xp[(size_t)(co + j) * HW] = acc[px][j];
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 conv_kernel(const float *__restrict__ y, const float *__restrict__ weight, float *__restrict__ x,
             int B, int C, int H, int W, int KH, int KW, int Cw, int Cg, int orient)
@@ -133,6 +223,32 @@ int launch_conv(const Geometry &g, const float *y, const float *weight, float *x
         dim3 grid(grid_x, g.groups);
         conv_tiled_kernel<<<grid, 256, smem, s>>>(y, weight, x, g.B, g.C, g.H, g.W, g.KH, g.KW, g.Cw, g.Cg, CgP4,
                                                   nsplit, g.orient);
+        return cuda_status(cudaGetLastError());
+    }
+    // (staging the weights per CTA only pays when a CTA has enough pixels to spread it over: measured
+    //  48.9 vs 24.9 us at (100,48,4,4), 24.8 vs 46.2 us at (256,24,8,8), 335 vs 1119 us at (512,48,16,16))
+    bool enough_pixels = (size_t)g.B * g.H * g.W >= (size_t)64 * kNumSM;
+    if (const char *e = getenv("IFK_CONV_WIDE")) enough_pixels = e[0] == '1';      // tests: pin / forbid the wide kernel
+    if (g.Cg > 16 && enough_pixels && smem <= (size_t)kMaxSmemBytes &&
+        (g.KW == 2 || g.KW == 3 || g.KW == 5 || g.KW == 7)) {
+        auto kern = g.KW == 2 ? conv_wide_kernel<2> : g.KW == 3 ? conv_wide_kernel<3>
+                  : g.KW == 5 ? conv_wide_kernel<5> : conv_wide_kernel<7>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        int per_sm = (int)((size_t)kMaxSmemBytes / (smem + 1024));
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        int grid_x = (kNumSM * per_sm + g.groups - 1) / g.groups;
+        const int items = g.H * ((g.W + 3) / 4) * (CgP4 >> 2);
+        int nsplit = (grid_x + g.B - 1) / g.B;                 // fill the GPU when the batch is small
+        const int max_split = (items + 255) / 256;
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit < 1) nsplit = 1;
+        if (grid_x > g.B * nsplit) grid_x = g.B * nsplit;
+        dim3 grid(grid_x, g.groups);
+        kern<<<grid, 256, smem, s>>>(y, weight, x, g.B, g.C, g.H, g.W, g.KH, g.Cw, g.Cg, CgP4, nsplit, g.orient);
         return cuda_status(cudaGetLastError());
     }
     size_t blocks = (total + 255) / 256;

@@ -206,6 +206,29 @@ def test_shuffle_kernel(IF, shape, nct, monkeypatch):
         assert_parity(run_all(IF, x[:4], w, g[:4], groups, orient=orient))
 
 
+@pytest.mark.parametrize("shape", [(3, 20, 10, 10, 3, 3, 1, 0.02), (2, 48, 9, 13, 3, 3, 1, 0.01), (2, 24, 8, 8, 2, 2, 1, 0.05),
+                                   (2, 32, 6, 7, 5, 5, 1, 0.005), (1, 17, 5, 3, 7, 7, 1, 0.005), (2, 80, 5, 6, 3, 3, 4, 0.02),
+                                   (200, 24, 8, 8, 3, 3, 1, 0.02)],
+                         ids=lambda s: "x".join(map(str, s[:7])))
+def test_wide_group_conv_kernel(IF, shape, monkeypatch):
+    """the register-tiled masked convolution for wide groups (4 pixels x 4 channels per thread, sliding
+    row window), pinned on small shapes, in every orientation, against the oracle and the plain kernel"""
+    B, C, H, W, KH, KW, groups, scale = shape
+    rng = np.random.default_rng(29)
+    y = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, KH, KW, scale)
+    yd, wd = dev(y), dev(w)
+    for orient in ("TL", "TR", "BL", "BR"):
+        monkeypatch.setenv("IFK_CONV_WIDE", "1")
+        a = IF.conv(yd, wd, groups=groups, orient=orient)
+        monkeypatch.setenv("IFK_CONV_WIDE", "0")
+        b = IF.conv(yd, wd, groups=groups, orient=orient)
+        torch.cuda.synchronize()
+        ref = oracle.conv(y.astype(np.float64), w.astype(np.float64), groups, threads=4, orient=orient)
+        assert oracle.max_rel_err(a.cpu().numpy(), ref) < TOL, orient
+        assert oracle.max_rel_err(b.cpu().numpy(), ref) < TOL, orient
+
+
 def test_bad_orient_is_rejected(IF):
     x = torch.randn(1, 4, 5, 5, device="cuda")
     w = torch.zeros(4, 4, 3, 3, device="cuda")
