@@ -138,3 +138,37 @@ def test_describe_solve_variants(lib, monkeypatch):
     monkeypatch.delenv("IFK_SOLVE_STREAM")
     monkeypatch.setenv("IFK_SOLVE_WINDOW", "1")
     assert d(3, 12, 16, 16, 3, 3, 12, 1).startswith("window<")
+
+
+def test_kernel_selection_is_well_formed_over_the_sweep_grid(lib):
+    """every cell of the microbenchmark grid (and around it) dispatches to a kernel whose launch
+    configuration is legal: threads <= 1024, shared memory <= 227 KB, cluster size <= 16 and dividing the
+    grid; the dW workspace and the prepared buffer have sizes; nothing needs a GPU"""
+    kinds = {}
+    for C in (1, 3, 4, 8, 12, 24, 48, 96):
+        for H in (1, 4, 7, 14, 16, 28, 32, 64, 128):
+            for k in (1, 2, 3, 5, 7):
+                for B in (1, 8, 100, 512):
+                    for groups in (1, 4):
+                        if C % groups:
+                            continue
+                        p = _native.problem(B, C, H, H, k, k, C, groups)
+                        d = _native.describe_solve(p)
+                        kind = d.split("<")[0].split(" ")[0]
+                        kinds[kind] = kinds.get(kind, 0) + 1
+                        assert kind in ("shfl", "smem", "window", "stream", "global"), d
+                        m = re.search(r"smem=(\d+)B", d)
+                        if m:
+                            assert int(m.group(1)) <= 227 * 1024, d
+                        m = re.search(r"threads=(\d+)(?:\+(\d+))?", d)
+                        assert m and int(m.group(1)) + int(m.group(2) or 0) <= 1024, d
+                        m = re.search(r"cluster=(\d+)", d)
+                        if m:
+                            cs = int(m.group(1))
+                            gx = int(re.search(r"grid=(\d+)x", d).group(1))
+                            assert cs in (1, 2, 4, 8, 16) and gx % cs == 0, d
+                        assert re.search(r"grid=(\d+)x(\d+)", d), d
+                        assert lib.ifk_prepared_floats(ctypes.byref(p)) > 0
+                        assert lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(p)) > 0
+    # the grid exercises every solve kernel
+    assert set(kinds) == {"shfl", "smem", "window", "stream", "global"}, kinds
