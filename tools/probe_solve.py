@@ -1,5 +1,6 @@
-"""Phase timing of the resident solve kernel (clock64 stamps of CTA 0): tuning aid.
+"""Phase timing of the resident and shuffle solve kernels (clock64 stamps of CTA 0, ifk_debug_set_probe).
     python tools/probe_solve.py B C H W k groups
+One launch after a device sync: the phases ahead of the loop run with cold caches.
 """
 import ctypes
 import os
@@ -13,6 +14,9 @@ from inverse_flow_b200.stack import reference_init_weight  # noqa: E402
 
 NAMES = ["start -> weights/T loaded, sync", "owner bookkeeping", "loop constants", "wait for the image (TMA)",
          "pre-pass z = T x", "diagonal loop", "ybuf re-zero / store issue", "store read wait"]
+# the shuffle kernel has no bookkeeping / pre-pass phases: those stamps coincide
+NAMES_SHFL = ["start -> weights/T in registers, PDL wait", "-", "-", "wait for the image (TMA)", "-",
+              "diagonal loop", "fence + TMA store issue", "store read wait"]
 
 
 def main():
@@ -36,8 +40,10 @@ def main():
     # stamps: 0 start, 1 tables, 2 weights, 3 ybuf zeroed, 4 landed, 5 loop start, 6 loop end, 7 store issued, 8 end
     order = [0, 1, 2, 3, 4, 5, 6, 7, 8]
     ndiag = H + W - 1
-    for a, b_, name in zip(order[:-1], order[1:], NAMES):
-        print("%-34s %8d cycles" % (name, t[b_] - t[a]))
+    desc = _native.describe_solve(_native.problem(B, C, H, W, k, k, C, g))
+    for a, b_, name in zip(order[:-1], order[1:], NAMES_SHFL if desc.startswith("shfl") else NAMES):
+        if name != "-":
+            print("%-42s %8d cycles" % (name, t[b_] - t[a]))
     print("total %d cycles; %.1f cycles per diagonal (%d diagonals)" % (t[8] - t[0], (t[6] - t[5]) / ndiag, ndiag))
 
 
