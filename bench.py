@@ -182,18 +182,23 @@ def cpu_stack_step(weights, xs, gs, groups_of, threads):
     return out
 
 
-def ref_cython_inverse_rate(weights, xs, budget_s=4.0):
-    """images/s of the reference's own compiled solver (oracle/_ref, float64, 1 core as the
-    reference builds it) on the forward solves of the stack; None if _ref is absent or the
-    stack is grouped (the Cython solver is full-C only)."""
+def ref_cython_inverse_rate(weights, xs, budget_s=4.0, module="solve_parallel_mc"):
+    """images/s of the reference's own compiled solver (oracle/_ref, float64) on the forward solves of
+    the stack: `solve_parallel_mc` as the reference builds it (no -fopenmp: its prange runs on 1 core)
+    or `solve_parallel_mc_omp` (same source with -fopenmp; num_threads=30 is hard-coded at .pyx:104 and
+    capped by the host).  None if _ref is absent or the stack is grouped (the solver is full-C only)."""
     try:
-        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
-        import solve_parallel_mc as cy
+        import importlib
+        ref_dir = os.path.join(ROOT, "oracle", "_ref")
+        if ref_dir not in sys.path:
+            sys.path.insert(0, ref_dir)
+        cy = importlib.import_module(module)
     except ImportError:
         return None
     t0 = time.perf_counter()
     n_img = 0
-    sample = max(1, min(8, xs[0].shape[0]))
+    # (the -fopenmp build spawns its 30-thread team once per anti-diagonal: ~2 images/s, so one image per pass)
+    sample = 1 if module.endswith("_omp") else max(1, min(8, xs[0].shape[0]))
     while time.perf_counter() - t0 < budget_s:
         for ws, x in zip(weights, xs):
             k = ws[0].shape[2]
@@ -277,7 +282,10 @@ def run_reference(args):
                          "sample": "full step (batch %d, all layers), float32 oracle port with OpenMP; the "
                                    "reference has no CPU backward" % batch,
                          "reference_cython_inverse_only_images_per_s":
-                             ref_cython_inverse_rate(weights, xs) if all(g == 1 for g in groups_of) else None},
+                             ref_cython_inverse_rate(weights, xs) if all(g == 1 for g in groups_of) else None,
+                         "reference_cython_openmp_inverse_only_images_per_s":
+                             ref_cython_inverse_rate(weights, xs, module="solve_parallel_mc_omp")
+                             if all(g == 1 for g in groups_of) else None},
         "gpu_launches": 0,
     })
     line["config"]["parallelism"] = "host cores of rank 0 only (%d OpenMP threads)" % threads
@@ -487,6 +495,9 @@ def run_ours(args):
             "ms_per_step": per * 1e3,
             "reference_cython_inverse_only_images_per_s":
                 ref_cython_inverse_rate(weights, xs) if all(g == 1 for g in groups_of) else None,
+            "reference_cython_openmp_inverse_only_images_per_s":
+                ref_cython_inverse_rate(weights, xs, module="solve_parallel_mc_omp")
+                if all(g == 1 for g in groups_of) else None,
         }
         line["parity"] = {"max_rel_err_vs_cpu_port_f32": float(max(errs)), "tolerance": 1e-5,
                           "what": "final y, dX and every dW of the chained stack"}
