@@ -120,3 +120,50 @@ def test_empty_batch():
     assert oracle.inverse(x, w).shape == (0, 4, 5, 5)
     dw = oracle.bwd_weight(x, x, w.shape)
     assert dw.shape == w.shape and np.all(dw == 0)
+
+
+@pytest.mark.parametrize("orient,pad,flip_axes", [
+    ("TL", (2, 0, 2, 0), ()),          # F.pad order: (left, right, top, bottom)
+    ("TR", (0, 2, 2, 0), (3,)),
+    ("BL", (2, 0, 0, 2), (2,)),
+    ("BR", (0, 2, 0, 2), (2, 3)),
+])
+def test_orientations_match_torch_conv2d_padded_towards_the_other_corner(orient, pad, flip_axes):
+    """orientation semantics, checked without any flip of the data: F L F is the masked convolution with
+    the zero padding on the opposite side(s) and the kernel reflected along the same axes (torch's
+    F.conv2d on CPU, float64); inverse and the gradients are then pinned to it through
+    conv(inverse(x)) == x and the adjoint / derivative identities."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(3)
+    for (B, C, H, W, groups) in [(2, 4, 6, 5, 1), (2, 8, 5, 7, 4)]:
+        y = rng.standard_normal((B, C, H, W))
+        w = make_weight(rng, C, C, 3, 3, 0.2).astype(np.float64)
+        wt = torch.from_numpy(oracle.masked_weight(w, groups))
+        if flip_axes:
+            wt = torch.flip(wt, flip_axes)
+        ref = F.conv2d(F.pad(torch.from_numpy(y), pad), wt, groups=groups).numpy()
+        got = oracle.conv(y, w, groups, orient=orient)
+        assert oracle.max_rel_err(got, ref) < 1e-13, orient
+        # the inverse undoes it, and the backward is its derivative
+        x = got
+        yy = oracle.inverse(x, w, groups, orient=orient)
+        assert oracle.max_rel_err(yy, y) < 1e-9
+        g = rng.standard_normal((B, C, H, W))
+        dx = oracle.bwd_input(g, w, groups, orient=orient)
+        xp = rng.standard_normal((B, C, H, W))
+        # adjoint identity <g, L^-1 x'> == <L^-T g, x'>
+        lhs = float(np.sum(g * oracle.inverse(xp, w, groups, orient=orient)))
+        rhs = float(np.sum(dx * xp))
+        assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
+        # dW by central differences of sum(g * inverse(x, W)) on a few live entries
+        dw = oracle.bwd_weight(dx, yy, w.shape, groups, orient=orient)
+        eps = 1e-6
+        Cg = C // groups
+        for (c, kc, a, b_) in [(1, 0, 0, 0), (C - 1, Cg - 1, 1, 2), (2, 1, 2, 1), (C - 1, 0, 2, 2)]:
+            wp, wm = w.copy(), w.copy()
+            wp[c, kc, a, b_] += eps
+            wm[c, kc, a, b_] -= eps
+            fd = (np.sum(g * oracle.inverse(x, wp, groups, orient=orient)) -
+                  np.sum(g * oracle.inverse(x, wm, groups, orient=orient))) / (2 * eps)
+            assert abs(fd - dw[c, kc, a, b_]) <= 1e-6 * max(1.0, abs(fd)), (orient, c, kc, a, b_)
