@@ -11,7 +11,6 @@ equal our inverse applied to g.  For C == 8 the literal inverse reads its own ch
 tests pin to the reference binary.  Square images only: the reference's diagonal indexing
 assumes H == W (kernel_general.cu:41-48).
 """
-import numpy as np
 import pytest
 import torch
 
