@@ -9,13 +9,16 @@
  * Conventions (all functions):
  *   - plain C, no torch / ATen types; every pointer is a DEVICE pointer to float32 data
  *     owned by the caller; nothing is allocated, freed or retained by the library;
- *   - tensors are NCHW-contiguous (the layout the reference passes, inv_conv.py:45-60);
+ *   - tensors are NCHW-contiguous (the layout the reference passes, inv_conv.py:45-60); a
+ *     channels_last (NHWC) activation must be made contiguous by the caller -- the Python
+ *     binding rejects it with IFK_ERR_BAD_LAYOUT instead of reading it as NCHW;
  *     the weight is (C, Cw, KH, KW) contiguous with Cw >= C/groups -- the reference layers
  *     pass Cw == C and the kernels read the first C/groups input columns of each row
  *     (inv_conv_with_bp_kernel_general.cu:62);
  *   - work is enqueued on the caller's stream and the call returns immediately: no device
  *     synchronisation (the reference calls cudaDeviceSynchronize() per diagonal, .cu:124),
- *     graph-capturable, re-entrant, no global state;
+ *     graph-capturable, re-entrant; the only process-wide state is the read-once cache of
+ *     the IFK_* test / tuning environment knobs (see ifk_debug_reload_env);
  *   - return value: 0 = ok, negative = IFK_ERR_* argument error (nothing was launched),
  *     positive = a cudaError_t raised by a launch.
  *
@@ -40,7 +43,7 @@
 extern "C" {
 #endif
 
-#define IFK_VERSION 200 /* major*10000 + minor*100 + patch */
+#define IFK_VERSION 300 /* major*10000 + minor*100 + patch */
 
 /* cudaStream_t without the CUDA headers (a driver-level CUstream handle). */
 typedef struct CUstream_st *ifk_stream_t;
@@ -52,7 +55,19 @@ enum ifk_status {
     IFK_ERR_BAD_GROUPS = -3,    /* groups < 1, C % groups != 0 or Cw < C/groups          */
     IFK_ERR_UNSUPPORTED = -4,   /* shape exceeds what the kernels address */
     IFK_ERR_NO_DEVICE = -5,     /* no CUDA device / driver                               */
-    IFK_ERR_BAD_ORIENT = -6     /* orient is not one of IFK_ORIENT_*                     */
+    IFK_ERR_BAD_ORIENT = -6,    /* orient is not one of IFK_ORIENT_*                     */
+    IFK_ERR_BAD_LAYOUT = -7,    /* a tensor is not NCHW-contiguous float32 (e.g. channels_last) */
+    IFK_ERR_BAD_FLAGS = -8      /* unknown bits in ifk_problem.flags                     */
+};
+
+/* ifk_problem.flags */
+enum ifk_flags {
+    /* The caller vouches that the operation enqueued on `stream` immediately before this call did
+     * NOT write the `prepared` buffer the call reads (true for every solve of a layer chain except
+     * the first one behind ifk_prepare*).  The solve kernels then fetch their weights ahead of the
+     * programmatic-dependent-launch wait, overlapping the previous kernel; without the flag the
+     * fetch happens after the wait (CUDA only guarantees a predecessor's writes after it). */
+    IFK_FLAG_STABLE_PREPARED = 1
 };
 
 /* Corner the causal support grows from (the reference layers' `order`, inf/layers/inv_conv.py:
@@ -74,6 +89,7 @@ typedef struct ifk_problem {
     int Cw;         /* second dimension of the weight tensor, >= C / groups     */
     int groups;     /* channel groups; the reference kernels hard-code 4        */
     int orient;     /* IFK_ORIENT_*; 0 for the plain top-left operator          */
+    int flags;      /* IFK_FLAG_* bits; 0 is always correct                     */
 } ifk_problem;
 
 int ifk_version(void);
@@ -144,12 +160,42 @@ int ifk_backward_f32(const ifk_problem *p, const float *g, const float *y,
  * e.g. "smem<cc=4,nv=6,vec=4> ns=4 nct=3 slots=16 iters=1 threads=192(192) ..." or "global ...". */
 int ifk_describe_solve(const ifk_problem *p, char *buf, size_t buflen);
 
-/* Phase timing of the resident and shuffle solve kernels: while `device_buffer` (16 x int64 of
- * device memory) is set, thread 0 of CTA (0,0) of every such solve writes clock64() stamps into
- * it -- 0 kernel start, 1..3 prologue done, 4 image landed, 5 / 6 diagonal loop start / end,
- * 7 store issued, 8 end.  NULL switches it off (the default).  Process-wide; a measuring aid
- * for bench.py's wavefront accounting and tools/probe_solve.py, not for concurrent use. */
-void ifk_debug_set_probe(long long *device_buffer);
+/* y = L^-1 x from the RAW weight in one call: prepare + solve, the exact shape of the reference's
+ * inverse(input, kernel, output) (inv_conv_with_bp_general.cpp:19-28).  `scratch` must hold
+ * ifk_prepared_floats(p) floats; it is left holding the prepared weights (usable by a following
+ * ifk_backward_f32). */
+int ifk_inverse_once_f32(const ifk_problem *p, const float *x, const float *weight, float *scratch,
+                         float *y, ifk_stream_t stream);
+
+/* Consecutive inverse-conv layers that feed each other directly -- the TL/TR/BL/BR layers of
+ * Inv_FlowUnit (inf/layers/inv_flow.py:28-53) -- as ONE launch: the image stays in shared memory
+ * from layer to layer, every layer's output ys[i] is still written (the backward needs it).
+ * Layer i uses orients[i] and prepared[i]; results are bit-identical to n ifk_inverse_f32 calls.
+ * p->orient is ignored.  IFK_ERR_UNSUPPORTED when the geometry has no resident kernel
+ * (callers then issue the n calls). */
+int ifk_inverse_chain_f32(const ifk_problem *p, int n, const int *orients, const float *const *prepared,
+                          const float *x, float *const *ys, ifk_stream_t stream);
+
+/* Phase timing of ONE solve (a debugging / measuring entry point, not part of the product path):
+ * like ifk_inverse_f32, and thread 0 of CTA (0,0) writes clock64() stamps into `probe` (16 x int64
+ * of device memory) -- 0 kernel start, 1..3 prologue done, 4 image landed, 5 / 6 diagonal loop
+ * start / end, 7 store issued, 8 end. */
+int ifk_inverse_probe_f32(const ifk_problem *p, const float *x, const float *prepared, float *y,
+                          long long *probe, ifk_stream_t stream);
+
+/* Measured denominators for the roofline (bench.py, tools/hw_microbench.py).  Both calls synchronise the
+ * device and are measuring aids, not part of the product path.
+ *   ifk_debug_fp32_peak: TFLOP/s of independent FP32 FMAs on all SMs -- out_tflops[0] scalar FFMA,
+ *     out_tflops[1] packed FFMA2; `scratch` >= 4 bytes of device memory.
+ *   ifk_debug_latencies: cycles per DEPENDENT operation, one CTA: host_out[0] FFMA, [1] FFMA2, [2] warp
+ *     shuffle, [3] shared-memory load, [4] st.shared -> __syncwarp -> ld.shared, [5] st.shared ->
+ *     bar.sync (8 warps) -> ld.shared, [6] bar.sync alone (8 warps), [7] FADD; `device_out` 16 x int64. */
+int ifk_debug_fp32_peak(float *scratch, double *out_tflops);
+int ifk_debug_latencies(long long *device_out, double *host_out);
+
+/* Re-read the IFK_* environment knobs (kernel pinning for tests and tuning runs).  They are parsed
+ * once per process and cached: no launch ever calls getenv(). */
+void ifk_debug_reload_env(void);
 
 #ifdef __cplusplus
 }

@@ -19,13 +19,16 @@ EXPORTS = (
     "ifk_version", "ifk_status_string", "ifk_prepared_floats", "ifk_prepare_f32", "ifk_prepare_many_f32",
     "ifk_inverse_f32", "ifk_conv_f32", "ifk_bwd_input_f32", "ifk_bwd_weight_workspace_bytes",
     "ifk_bwd_weight_f32", "ifk_bwd_weight_partial_f32", "ifk_bwd_weight_reduce_many_f32",
-    "ifk_backward_f32", "ifk_describe_solve", "ifk_debug_set_probe",
+    "ifk_backward_f32", "ifk_describe_solve", "ifk_inverse_once_f32", "ifk_inverse_chain_f32",
+    "ifk_inverse_probe_f32", "ifk_debug_reload_env", "ifk_debug_fp32_peak", "ifk_debug_latencies",
 )
+
+FLAG_STABLE_PREPARED = 1        # enum ifk_flags
 
 
 class Problem(ctypes.Structure):
     """struct ifk_problem"""
-    _fields_ = [(n, ctypes.c_int) for n in ("B", "C", "H", "W", "KH", "KW", "Cw", "groups", "orient")]
+    _fields_ = [(n, ctypes.c_int) for n in ("B", "C", "H", "W", "KH", "KW", "Cw", "groups", "orient", "flags")]
 
 
 class IfkError(RuntimeError):
@@ -66,6 +69,18 @@ def load():
     lib.ifk_bwd_weight_reduce_many_f32.argtypes = [P, ci, vp, sz, vp, sz, vp]
     lib.ifk_describe_solve.restype = ci
     lib.ifk_describe_solve.argtypes = [P, ctypes.c_char_p, sz]
+    lib.ifk_inverse_once_f32.restype = ci
+    lib.ifk_inverse_once_f32.argtypes = [P, vp, vp, vp, vp, vp]
+    lib.ifk_inverse_chain_f32.restype = ci
+    lib.ifk_inverse_chain_f32.argtypes = [P, ci, ctypes.POINTER(ci), ctypes.POINTER(vp), vp, ctypes.POINTER(vp), vp]
+    lib.ifk_inverse_probe_f32.restype = ci
+    lib.ifk_inverse_probe_f32.argtypes = [P, vp, vp, vp, vp, vp]
+    lib.ifk_debug_reload_env.restype = None
+    lib.ifk_debug_reload_env.argtypes = []
+    lib.ifk_debug_fp32_peak.restype = ci
+    lib.ifk_debug_fp32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    lib.ifk_debug_latencies.restype = ci
+    lib.ifk_debug_latencies.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 
@@ -90,8 +105,36 @@ def orient_code(orient):
     return int(orient)
 
 
-def problem(B, C, H, W, KH, KW, Cw, groups, orient=0):
-    return Problem(int(B), int(C), int(H), int(W), int(KH), int(KW), int(Cw), int(groups), orient_code(orient))
+def problem(B, C, H, W, KH, KW, Cw, groups, orient=0, flags=0):
+    return Problem(int(B), int(C), int(H), int(W), int(KH), int(KW), int(Cw), int(groups), orient_code(orient),
+                   int(flags))
+
+
+def with_flags(p, flags):
+    """a copy of the problem with other IFK_FLAG_* bits"""
+    return Problem(p.B, p.C, p.H, p.W, p.KH, p.KW, p.Cw, p.groups, p.orient, int(flags))
+
+
+def reload_env():
+    """re-read the IFK_* knobs (they are cached by the library; tests pin kernels through them)"""
+    load().ifk_debug_reload_env()
+
+
+def hw_microbench(device=None):
+    """measured roofline denominators of this GPU: FP32 FMA rate (TFLOP/s) and the latencies (cycles) of the
+    instructions a wavefront step chains.  Synchronises; a measuring aid for bench.py / tools."""
+    lib = load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        buf = torch.zeros(16, dtype=torch.int64, device=device)
+        tf = (ctypes.c_double * 2)()
+        lat = (ctypes.c_double * 8)()
+        torch.cuda.synchronize()
+        check(lib.ifk_debug_fp32_peak(ctypes.c_void_p(buf.data_ptr()), tf))
+        check(lib.ifk_debug_latencies(ctypes.c_void_p(buf.data_ptr()), lat))
+    names = ["ffma", "ffma2", "shfl", "lds", "sts_syncwarp_lds", "sts_barsync8_lds", "barsync8", "fadd"]
+    return {"fp32_tflops_ffma": tf[0], "fp32_tflops_ffma2": tf[1],
+            "latency_cycles": {n: lat[i] for i, n in enumerate(names)}}
 
 
 def current_stream(device):

@@ -1,5 +1,6 @@
 // extern "C" boundary (include/ifk.h): argument validation and dispatch only.
 #include <stdio.h>
+#include "ifk_env.cuh"
 #include "ifk_internal.cuh"
 
 namespace ifk {
@@ -12,7 +13,8 @@ int make_geometry(const ifk_problem *p, Geometry *g)
     if (p->groups < 1 || p->C % p->groups != 0 || p->Cw < p->C / p->groups) return IFK_ERR_BAD_GROUPS;
     g->B = p->B; g->C = p->C; g->H = p->H; g->W = p->W; g->KH = p->KH; g->KW = p->KW;
     if (p->orient < 0 || p->orient > 3) return IFK_ERR_BAD_ORIENT;
-    g->Cw = p->Cw; g->groups = p->groups; g->orient = p->orient;
+    if (p->flags & ~IFK_FLAG_STABLE_PREPARED) return IFK_ERR_BAD_FLAGS;
+    g->Cw = p->Cw; g->groups = p->groups; g->orient = p->orient; g->flags = p->flags;
     g->Cg = p->C / p->groups;
     g->K = p->KH * p->KW;
     // 32-bit index arithmetic inside one image / one weight tensor
@@ -46,6 +48,8 @@ const char *ifk_status_string(int status)
         case IFK_ERR_UNSUPPORTED: return "shape not supported by the kernels";
         case IFK_ERR_NO_DEVICE: return "no CUDA device";
         case IFK_ERR_BAD_ORIENT: return "bad orient: need one of IFK_ORIENT_TL/TR/BL/BR (0..3)";
+        case IFK_ERR_BAD_LAYOUT: return "bad layout: tensors must be NCHW-contiguous float32 (channels_last is not accepted)";
+        case IFK_ERR_BAD_FLAGS: return "bad flags: unknown IFK_FLAG_* bits";
     }
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
     return "unknown ifk status";
@@ -86,7 +90,7 @@ int ifk_inverse_f32(const ifk_problem *p, const float *x, const float *prepared,
     int st = make_geometry(p, &g);
     if (st != IFK_OK) return st;
     if (!prepared || (g.B > 0 && (!x || !y))) return IFK_ERR_NULL_POINTER;
-    return launch_solve(g, x, prepared_dir(g, prepared, 0), y, false, (cudaStream_t)stream);
+    return launch_solve(g, x, prepared, y, false, (cudaStream_t)stream);
 }
 
 int ifk_conv_f32(const ifk_problem *p, const float *y, const float *weight, float *x,
@@ -106,7 +110,7 @@ int ifk_bwd_input_f32(const ifk_problem *p, const float *grad, const float *prep
     int st = make_geometry(p, &g);
     if (st != IFK_OK) return st;
     if (!prepared || (g.B > 0 && (!grad || !dx))) return IFK_ERR_NULL_POINTER;
-    return launch_solve(g, grad, prepared_dir(g, prepared, 1), dx, true, (cudaStream_t)stream);
+    return launch_solve(g, grad, prepared, dx, true, (cudaStream_t)stream);
 }
 
 size_t ifk_bwd_weight_workspace_bytes(const ifk_problem *p)
@@ -157,9 +161,47 @@ int ifk_backward_f32(const ifk_problem *p, const float *grad, const float *y, co
     return ifk_bwd_weight_f32(p, dx, y, dw, workspace, stream);
 }
 
-// Measuring aid (ifk.h, "introspection"): device buffer of >= 16 int64 that CTA (0,0) of the
-// next solve launches fills with clock64() stamps of its phases (nullptr switches it off).
-void ifk_debug_set_probe(long long *device_buffer) { set_solve_probe(device_buffer); }
+int ifk_inverse_once_f32(const ifk_problem *p, const float *x, const float *weight, float *scratch, float *y,
+                         ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!weight || !scratch || (g.B > 0 && (!x || !y))) return IFK_ERR_NULL_POINTER;
+    st = launch_prepare(g, weight, scratch, (cudaStream_t)stream);
+    if (st != IFK_OK) return st;
+    g.flags &= ~IFK_FLAG_STABLE_PREPARED;        // the prepare kernel is this solve's predecessor
+    return launch_solve(g, x, scratch, y, false, (cudaStream_t)stream);
+}
+
+int ifk_inverse_chain_f32(const ifk_problem *p, int n, const int *orients, const float *const *prepared,
+                          const float *x, float *const *ys, ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (n < 0) return IFK_ERR_BAD_SHAPE;
+    if (n == 0) return IFK_OK;
+    if (!orients || !prepared || !ys || (g.B > 0 && !x)) return IFK_ERR_NULL_POINTER;
+    for (int i = 0; i < n; i++) {
+        if (orients[i] < 0 || orients[i] > 3) return IFK_ERR_BAD_ORIENT;
+        if (!prepared[i] || (g.B > 0 && !ys[i])) return IFK_ERR_NULL_POINTER;
+    }
+    return launch_solve_chain(g, n, orients, prepared, x, ys, (cudaStream_t)stream);
+}
+
+// Measuring aid (ifk.h): one solve whose CTA (0,0) stamps clock64() at its phase boundaries.
+int ifk_inverse_probe_f32(const ifk_problem *p, const float *x, const float *prepared, float *y,
+                          long long *probe, ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if (!prepared || !probe || (g.B > 0 && (!x || !y))) return IFK_ERR_NULL_POINTER;
+    return launch_solve(g, x, prepared, y, false, (cudaStream_t)stream, probe);
+}
+
+void ifk_debug_reload_env(void) { reload_env(); }
 
 int ifk_describe_solve(const ifk_problem *p, char *buf, size_t buflen)
 {

@@ -13,6 +13,7 @@
 //          consumed.  One recursive-halving shuffle reduction at the very end.
 // Stage 2  bwd_weight_reduce_kernel: sums the per-chunk partials in chunk order (fixed order,
 //          no atomics -> bit-reproducible), negates, masks, scatters into the weight layout.
+#include "ifk_env.cuh"
 #include "ifk_solve_kernel.cuh"   // TMA / mbarrier primitives
 
 namespace ifk {
@@ -263,7 +264,6 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
     int off, size;
     rs_owner(TC * TK, 32, lane, &off, &size);
     float *out = p.partial + ((size_t)chunk * p.C + (size_t)G * Cg) * Cg * K;   // [c][kc][t]
-#pragma unroll
     constexpr int kFinal = halve_final(TC * TK, 32);
 #pragma unroll
     for (int i = 0; i < kFinal; i++) {
@@ -345,7 +345,7 @@ int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y
     p.w_magic = g.W > 1 ? (unsigned)((0x100000000ULL + g.W - 1) / g.W) : 0u;      // 0: single column
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) ? 1 : 0;
-    if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
+    if (env().nobulk) p.bulk = 0;
     dim3 grid(pl.nchunks, g.groups, pl.nz);
     void (*kern)(const BwdWeightParams) = nullptr;
     if (pl.tc == 4 && pl.tk == 12) kern = bwd_weight_partial_kernel<4, 12>;

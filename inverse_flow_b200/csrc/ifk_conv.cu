@@ -14,6 +14,7 @@
 // conv_kernel: one thread per output, everything through L1/L2 -- single-channel groups and whatever the
 // staged kernels cannot hold.
 #include <stdlib.h>
+#include "ifk_env.cuh"
 #include "ifk_internal.cuh"
 
 namespace ifk {
@@ -228,7 +229,7 @@ int launch_conv(const Geometry &g, const float *y, const float *weight, float *x
     // (staging the weights per CTA only pays when a CTA has enough pixels to spread it over: measured
     //  48.9 vs 24.9 us at (100,48,4,4), 24.8 vs 46.2 us at (256,24,8,8), 335 vs 1119 us at (512,48,16,16))
     bool enough_pixels = (size_t)g.B * g.H * g.W >= (size_t)64 * kNumSM;
-    if (const char *e = getenv("IFK_CONV_WIDE")) enough_pixels = e[0] == '1';      // tests: pin / forbid the wide kernel
+    if (env().conv_wide >= 0) enough_pixels = env().conv_wide == 1;      // tests: pin / forbid the wide kernel
     if (g.Cg > 16 && enough_pixels && smem <= (size_t)kMaxSmemBytes &&
         (g.KW == 2 || g.KW == 3 || g.KW == 5 || g.KW == 7)) {
         auto kern = g.KW == 2 ? conv_wide_kernel<2> : g.KW == 3 ? conv_wide_kernel<3>

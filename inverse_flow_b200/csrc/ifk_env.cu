@@ -1,0 +1,85 @@
+// IFK_* knobs: parsed once, cached (see ifk_env.cuh).
+#include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "ifk_env.cuh"
+#include "ifk_internal.cuh"
+
+namespace ifk {
+
+static EnvKnobs g_env;
+static std::once_flag g_env_once;
+static std::mutex g_env_mutex;
+
+static bool is_one(const char *name)
+{
+    const char *e = getenv(name);
+    return e && e[0] == '1';
+}
+static bool is_zero(const char *name)
+{
+    const char *e = getenv(name);
+    return e && e[0] == '0';
+}
+
+static void parse_env()
+{
+    EnvKnobs k{};
+    k.solve_global = is_one("IFK_SOLVE_GLOBAL");
+    k.solve_stream = is_one("IFK_SOLVE_STREAM");
+    k.solve_window = is_one("IFK_SOLVE_WINDOW");
+    k.shfl_off = is_zero("IFK_SOLVE_SHFL");
+    k.wave_off = is_zero("IFK_SOLVE_WAVE");
+    k.nobulk = is_one("IFK_SOLVE_NOBULK");
+    k.pdl = !is_zero("IFK_PDL");
+    if (const char *e = getenv("IFK_SHFL_NCT")) k.shfl_nct = atoi(e);
+    k.conv_wide = -1;
+    if (const char *e = getenv("IFK_CONV_WIDE")) k.conv_wide = e[0] == '1' ? 1 : 0;
+    if (const char *e = getenv("IFK_SOLVE_CFG"))
+        k.has_solve_cfg = *e && sscanf(e, "%d,%d,%d,%d,%d", &k.solve_cfg[0], &k.solve_cfg[1], &k.solve_cfg[2],
+                                       &k.solve_cfg[3], &k.solve_cfg[4]) == 5;
+    if (const char *e = getenv("IFK_STREAM_CFG")) sscanf(e, "%d,%d", &k.stream_cfg[0], &k.stream_cfg[1]);
+    if (const char *e = getenv("IFK_WINDOW_CFG"))
+        sscanf(e, "%d,%d,%d,%d", &k.window_cfg[0], &k.window_cfg[1], &k.window_cfg[2], &k.window_cfg[3]);
+    if (const char *e = getenv("IFK_WAVE_CFG"))
+        sscanf(e, "%d,%d,%d,%d", &k.wave_cfg[0], &k.wave_cfg[1], &k.wave_cfg[2], &k.wave_cfg[3]);
+    std::lock_guard<std::mutex> lock(g_env_mutex);
+    g_env = k;
+}
+
+const EnvKnobs &env()
+{
+    std::call_once(g_env_once, parse_env);
+    return g_env;
+}
+
+void reload_env()
+{
+    std::call_once(g_env_once, parse_env);
+    parse_env();
+}
+
+static int query_attr(cudaDeviceAttr attr, int fallback)
+{
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, attr, dev) != cudaSuccess || v <= 0) {
+        cudaGetLastError();      // no device (host-only introspection): the B200 figures
+        return fallback;
+    }
+    return v;
+}
+
+int device_sm_count()
+{
+    static int v = query_attr(cudaDevAttrMultiProcessorCount, kNumSM);
+    return v;
+}
+
+int device_max_smem_optin()
+{
+    static int v = query_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, kMaxSmemBytes);
+    return v;
+}
+
+}  // namespace ifk

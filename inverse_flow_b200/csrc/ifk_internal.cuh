@@ -12,6 +12,7 @@ constexpr int kMaxSmemBytes = 227 * 1024; // opt-in dynamic shared memory per CT
 struct Geometry {
     int B, C, H, W, KH, KW, Cw, groups;
     int orient;  // IFK_ORIENT_*: bit 0 reflects W, bit 1 reflects H
+    int flags;   // IFK_FLAG_*
     int Cg;   // channels per group
     int K;    // KH * KW taps (tap 0 = the centre / "x" tap)
     int KD;   // K * Cg : length of one prepared weight row
@@ -21,7 +22,8 @@ struct Geometry {
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 int make_geometry(const ifk_problem *p, Geometry *g);          // validates; IFK_ERR_* or 0
-inline size_t prepared_floats(const Geometry &g) { return (size_t)2 * g.C * g.KDP; }
+size_t prepared_floats(const Geometry &g);                      // canonical rows + the wave kernel's packed copy
+int launch_wave_pack(const Geometry &g, float *prepared, int count, size_t prepared_stride, cudaStream_t s);
 inline const float *prepared_dir(const Geometry &g, const float *prepared, int dir) {
     return prepared + (size_t)dir * g.C * g.KDP;
 }
@@ -29,8 +31,8 @@ inline const float *prepared_dir(const Geometry &g, const float *prepared, int d
 // launchers (each returns 0 or a cudaError_t)
 int launch_prepare(const Geometry &g, const float *weight, float *prepared, cudaStream_t s, int count = 1,
                    size_t weight_stride = 0, size_t prepared_stride = 0);
-int launch_solve(const Geometry &g, const float *in, const float *prep_dir, float *out,
-                 bool reverse, cudaStream_t s);
+int launch_solve(const Geometry &g, const float *in, const float *prepared, float *out,
+                 bool reverse, cudaStream_t s, long long *probe = nullptr);     // `prepared`: the whole buffer
 int launch_conv(const Geometry &g, const float *y, const float *weight, float *x, cudaStream_t s);
 size_t bwd_weight_workspace_bytes(const Geometry &g);
 int launch_bwd_weight(const Geometry &g, const float *dx, const float *y, float *dw,
@@ -50,9 +52,13 @@ int launch_solve_window(const Geometry &g, const float *in, const float *prep_di
 bool shfl_solve_available(const Geometry &g);
 int describe_shfl_solve(const Geometry &g, char *buf, size_t buflen);
 int launch_solve_shfl(const Geometry &g, const float *in, const float *prep_dir, float *out, bool reverse,
-                      cudaStream_t s);
-void set_solve_probe(long long *device_buffer);
-long long *get_solve_probe();
+                      long long *probe, cudaStream_t s);
+int launch_solve_chain(const Geometry &g, int n, const int *orients, const float *const *prepared, const float *x,
+                       float *const *ys, cudaStream_t s);
+bool wave_solve_available(const Geometry &g);
+int describe_wave_solve(const Geometry &g, char *buf, size_t buflen);
+int launch_solve_wave(const Geometry &g, const float *in, const float *prepared, float *out, bool reverse,
+                      int flags, long long *probe, cudaStream_t s);
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 

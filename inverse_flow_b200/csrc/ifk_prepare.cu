@@ -132,7 +132,10 @@ int launch_prepare(const Geometry &g, const float *weight, float *prepared, cuda
     prepare_kernel<<<grid, kPrepThreads, smem, s>>>(weight, prepared, g.C, g.Cg, g.Cw, g.KH, g.KW, g.KD,
                                                     g.KDP, taps_per_cta, g.groups, weight_stride,
                                                     prepared_stride);
-    return cuda_status(cudaGetLastError());
+    const int st = cuda_status(cudaGetLastError());
+    if (st != 0) return st;
+    // the pipelined wavefront kernel reads a lane-major packed copy of these rows (ifk_solve_wave.cu)
+    return launch_wave_pack(g, prepared, count, prepared_stride, s);
 }
 
 }  // namespace ifk

@@ -6,6 +6,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include "ifk_env.cuh"
 #include "ifk_solve_kernel.cuh"
 
 namespace ifk {
@@ -82,24 +86,21 @@ static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) l++; return l; 
 
 static bool parse_forced(int *cc, int *nv, int *vec, int *ns, int *nslots)
 {
-    const char *e = getenv("IFK_SOLVE_CFG");   // "cc,nv,vec,ns,nslots" -- tuning experiments only
-    if (!e || !*e) return false;
-    return sscanf(e, "%d,%d,%d,%d,%d", cc, nv, vec, ns, nslots) == 5;
+    const EnvKnobs &k = env();                 // IFK_SOLVE_CFG="cc,nv,vec,ns,nslots" -- tuning experiments only
+    if (!k.has_solve_cfg) return false;
+    *cc = k.solve_cfg[0]; *nv = k.solve_cfg[1]; *vec = k.solve_cfg[2]; *ns = k.solve_cfg[3]; *nslots = k.solve_cfg[4];
+    return true;
 }
 
-static SolveConfig choose_config(const Geometry &g)
+static SolveConfig choose_config_uncached(const Geometry &g)
 {
     SolveConfig best{};
     best.smem = false;
     best.threads = 512;
     best.grid_x = g.B < 4 * kNumSM ? g.B : 4 * kNumSM;
     if (best.grid_x < 1) best.grid_x = 1;
-    const char *force_global = getenv("IFK_SOLVE_GLOBAL");      // testing: the plain fallback kernel
-    const char *force_stream = getenv("IFK_SOLVE_STREAM");      // testing: the stream kernel
-    const char *force_window = getenv("IFK_SOLVE_WINDOW");      // testing: the window kernel
-    if ((force_global && force_global[0] == '1') || (force_stream && force_stream[0] == '1') ||
-        (force_window && force_window[0] == '1'))
-        return best;
+    const EnvKnobs &knobs = env();              // testing: pin the fallback / stream / window kernel
+    if (knobs.solve_global || knobs.solve_stream || knobs.solve_window) return best;
 
     const int HP = g.H + g.KH - 1, WP = g.W + g.KW - 1;
     const int XN = round_up(g.Cg * g.H * g.W, 4);
@@ -196,13 +197,35 @@ static SolveConfig choose_config(const Geometry &g)
     return best;
 }
 
+// memoised per geometry: the search above costs 20-30 us on the host, a launch must not
+static SolveConfig choose_config(const Geometry &g)
+{
+    typedef std::tuple<int, int, int, int, int, int, int> Key;
+    static std::map<Key, SolveConfig> cache;
+    static std::mutex mu;
+    static EnvKnobs seen;
+    static bool have_seen = false;
+    const EnvKnobs &k = env();
+    const int bcap = 4 * kNumSM;
+    const Key key(g.Cg, g.H, g.W, g.KH, g.KW, g.groups, g.B < bcap ? g.B : bcap);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!have_seen || memcmp(&seen, &k, sizeof(EnvKnobs)) != 0) {     // knobs reloaded (tests): start over
+        cache.clear();
+        seen = k;
+        have_seen = true;
+    }
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const SolveConfig c = choose_config_uncached(g);
+    cache[key] = c;
+    return c;
+}
+
 bool solve_use_pdl()
 {
-    // programmatic dependent launch of the resident solve: the next solve's prologue (weights ->
-    // registers, zero fill) overlaps the current solve's wavefront: 0.430 -> 0.399 ms per glow_mnist
-    // step, 5.19 -> 4.80 ms per glow_imagenet32 step.  IFK_PDL=0 switches it off.
-    const char *e = getenv("IFK_PDL");
-    return !(e && e[0] == '0');
+    // programmatic dependent launch of the solves: the next solve's prologue (weights -> registers,
+    // zero fill) overlaps the current solve's wavefront.  IFK_PDL=0 switches it off.
+    return env().pdl;
 }
 
 // which kernel serves an image that is not shared-memory resident: 2 = window (ring of diagonals
@@ -210,31 +233,28 @@ bool solve_use_pdl()
 // 0 = the plain fallback.  IFK_SOLVE_GLOBAL / IFK_SOLVE_STREAM = 1 pin the older kernels (tests).
 static int large_image_kernel(const Geometry &g)
 {
-    const char *force_global = getenv("IFK_SOLVE_GLOBAL");
-    if (force_global && force_global[0] == '1') return 0;
-    const char *force_stream = getenv("IFK_SOLVE_STREAM");
-    const bool pin_stream = force_stream && force_stream[0] == '1';
-    if (!pin_stream && window_solve_available(g)) return 2;
+    const EnvKnobs &k = env();
+    if (k.solve_global) return 0;
+    if (!k.solve_stream && window_solve_available(g)) return 2;
     if (stream_solve_available(g)) return 1;
     return 0;
 }
 
-static long long *g_probe = nullptr;   // tuning aid, see ifk_debug_set_probe
-void set_solve_probe(long long *p) { g_probe = p; }
-long long *get_solve_probe() { return g_probe; }
-
-int launch_solve(const Geometry &g, const float *in, const float *prep_dir, float *out,
-                 bool reverse, cudaStream_t s)
+int launch_solve(const Geometry &g, const float *in, const float *prepared, float *out,
+                 bool reverse, cudaStream_t s, long long *probe)
 {
     if (g.B == 0) return 0;
-    if (shfl_solve_available(g)) return launch_solve_shfl(g, in, prep_dir, out, reverse, s);
+    const float *prep_dir = prepared_dir(g, prepared, reverse ? 1 : 0);
+    if (shfl_solve_available(g)) return launch_solve_shfl(g, in, prep_dir, out, reverse, probe, s);
+    if (wave_solve_available(g)) return launch_solve_wave(g, in, prepared, out, reverse, g.flags, probe, s);
     const SolveConfig c = choose_config(g);
     SolveParams p{};
     p.in = in; p.out = out; p.prep = prep_dir;
     p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.KH = g.KH; p.KW = g.KW;
     p.Cg = g.Cg; p.KD = g.KD; p.KDP = g.KDP;
     p.flip = reverse ? (g.orient ^ 3) : g.orient;     // the adjoint walks the fully reflected frame
-    p.probe = g_probe;
+    p.probe = probe;
+    p.early = (g.flags & IFK_FLAG_STABLE_PREPARED) ? 1 : 0;
     dim3 grid(c.grid_x, g.groups);
     if (!c.smem) {
         switch (large_image_kernel(g)) {
@@ -250,7 +270,7 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
     p.v_dt = c.ns / c.CgV; p.v_dq = c.ns % c.CgV;
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0) ? 1 : 0;
-    if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
+    if (env().nobulk) p.bulk = 0;
     p.walign = ((uintptr_t)prep_dir % 16 == 0) ? 1 : 0;
     switch (c.vec) {
         case 1: return launch_solve_vec1(c.cc, c.nv, p, grid, c.threads, c.smem_bytes, s);
@@ -263,6 +283,7 @@ int launch_solve(const Geometry &g, const float *in, const float *prep_dir, floa
 int describe_solve(const Geometry &g, char *buf, size_t buflen)
 {
     if (shfl_solve_available(g)) return describe_shfl_solve(g, buf, buflen);
+    if (wave_solve_available(g)) return describe_wave_solve(g, buf, buflen);
     const SolveConfig c = choose_config(g);
     if (c.smem)
         snprintf(buf, buflen, "smem<cc=%d,nv=%d,vec=%d> ns=%d nct=%d slots=%d iters=%d threads=%d(%d) smem=%zuB grid=%dx%d",

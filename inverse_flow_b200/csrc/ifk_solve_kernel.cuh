@@ -45,6 +45,7 @@ struct SolveParams {
                         // (adjoint solve = both reflected; IFK_ORIENT_* reflections are XORed in)
     int bulk;           // image size / pointers allow TMA bulk copies (16-byte granularity)
     int walign;         // prepared weights are 16-byte aligned (128-bit weight loads allowed)
+    int early;          // IFK_FLAG_STABLE_PREPARED: weights may be fetched ahead of griddepcontrol.wait
     long long *probe;   // tuning aid: clock64() stamps of CTA (0,0) thread 0, or nullptr
 };
 
@@ -264,13 +265,16 @@ solve_smem_kernel(const SolveParams p)
     const float *in0 = p.in + (size_t)G * Cg * HW;
     float *out0 = p.out + (size_t)G * Cg * HW;
 
-    // Programmatic dependent launch: let the next kernel of the stream start launching now, and do
-    // everything that does not depend on the previous kernel's output before waiting for it: the
-    // shared-memory zero fill and -- the expensive part -- fetching this thread's weight slice and T.
-    // Reading the prepared weights ahead of the wait is safe because the only kernels that write
-    // them (prepare_kernel) never trigger programmatic completion: a solve launched behind a prepare
-    // does not start before the prepare has finished.  Both instructions are no-ops in a plain launch.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Programmatic dependent launch: everything that does not depend on the previous kernel's output
+    // happens before the dependency wait: the shared-memory zero fill and -- only when the caller
+    // vouches that the previous operation of the stream did not write the prepared weights
+    // (IFK_FLAG_STABLE_PREPARED, ifk.h) -- fetching this thread's weight slice and T.  Without the flag
+    // the fetch follows the wait: CUDA guarantees a predecessor's writes only after it.  The dependents
+    // are released after the wait, so the guarantee is transitive along a chain of solves.
+    if (!p.early) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     if (tid == 0) smem[2] = 0.f;          // source of the opaque zero used by Hold (see above)
 
     // ybuf starts from zero for every image: the halo, and the not-yet-written interior that
@@ -339,7 +343,10 @@ solve_smem_kernel(const SolveParams p)
             const int ci = i / p.CgP4, co = i - ci * p.CgP4;
             tT[i] = co < Cg ? __ldg(wg + (size_t)co * p.KDP + ci) : 0.f;
         }
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // the input image may only be touched from here on
+    if (p.early) {                                          // the input image may only be touched from here on
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     if (p.bulk && tid == 0) {
         mbar_init(bar, 1);
         if (b < p.B) {

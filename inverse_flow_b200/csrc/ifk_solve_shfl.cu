@@ -27,6 +27,7 @@
 // (inv_conv_with_bp_kernel_general.cu:72-129; adjoint: .cu:388-483).
 #include <stdio.h>
 #include <stdlib.h>
+#include "ifk_env.cuh"
 #include "ifk_solve_kernel.cuh"
 
 namespace ifk {
@@ -38,6 +39,7 @@ struct ShflParams {
     int B, C, H, W, KDP, CgP4, XN;
     int flip;           // as SolveParams::flip
     int bulk;
+    int early;          // IFK_FLAG_STABLE_PREPARED: weights may be fetched ahead of griddepcontrol.wait
     long long *probe;   // tuning aid: clock64() stamps of CTA (0,0) lane 0 (same slots as the resident kernel)
 };
 
@@ -89,9 +91,12 @@ solve_shfl_kernel(const ShflParams p)
     const float *in0 = p.in + (size_t)G * CG * HW;
     float *out0 = p.out + (size_t)G * CG * HW;
 
-    // programmatic dependent launch: as in the resident kernel, everything that does not read the
-    // previous kernel's output (this lane's weights and rows of T -> registers) happens before the wait
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // programmatic dependent launch: as in the resident kernel, this lane's weights and rows of T are
+    // fetched ahead of the dependency wait only under IFK_FLAG_STABLE_PREPARED (ifk.h)
+    if (!p.early) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     const int row = lane / NCT, ct = lane - row * NCT;
     const bool valid = row < H;
@@ -117,7 +122,10 @@ solve_shfl_kernel(const ShflParams p)
             treg[i][e] = E::make(tmp);
         }
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.early) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     int b = blockIdx.x;
     if (p.bulk && lane == 0) {
         mbar_init(bar, 1);
@@ -334,14 +342,9 @@ static ShflConfig choose_shfl(const Geometry &g)
 {
     ShflConfig c{};
     c.ok = false;
-    const char *off = getenv("IFK_SOLVE_SHFL");
-    if (off && off[0] == '0') return c;
-    for (const char *name : {"IFK_SOLVE_GLOBAL", "IFK_SOLVE_STREAM", "IFK_SOLVE_WINDOW", "IFK_SOLVE_CFG"}) {
-        const char *e = getenv(name);               // tests / tuning runs that pin another kernel
-        if (e && e[0] && e[0] != '0') return c;
-    }
-    int want_nct = 0;
-    if (const char *e = getenv("IFK_SHFL_NCT")) want_nct = atoi(e);     // tuning only
+    const EnvKnobs &k = env();
+    if (k.shfl_off || k.pins_other_solver()) return c;          // tests / tuning runs that pin another kernel
+    const int want_nct = k.shfl_nct;                            // tuning only
     const int XN = round_up(g.Cg * g.H * g.W, 4);
     const size_t smem = 16 + (size_t)XN * sizeof(float);
     if (smem > (size_t)kMaxSmemBytes) return c;
@@ -376,7 +379,7 @@ int describe_shfl_solve(const Geometry &g, char *buf, size_t buflen)
 }
 
 int launch_solve_shfl(const Geometry &g, const float *in, const float *prep_dir, float *out, bool reverse,
-                      cudaStream_t s)
+                      long long *probe, cudaStream_t s)
 {
     const ShflConfig c = choose_shfl(g);
     if (!c.ok) return IFK_ERR_UNSUPPORTED;
@@ -388,8 +391,9 @@ int launch_solve_shfl(const Geometry &g, const float *in, const float *prep_dir,
     p.flip = reverse ? (g.orient ^ 3) : g.orient;
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && (((uintptr_t)in | (uintptr_t)out) % 16 == 0) ? 1 : 0;
-    if (const char *nb = getenv("IFK_SOLVE_NOBULK")) if (nb[0] == '1') p.bulk = 0;
-    p.probe = get_solve_probe();
+    if (env().nobulk) p.bulk = 0;
+    p.early = (g.flags & IFK_FLAG_STABLE_PREPARED) ? 1 : 0;
+    p.probe = probe;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c.grid_x, g.groups);
     cfg.blockDim = dim3(32);

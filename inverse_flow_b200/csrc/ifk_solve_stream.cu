@@ -19,6 +19,7 @@
 // (inv_conv_with_bp_kernel_general.cu:72-129).
 #include <stdio.h>
 #include <stdlib.h>
+#include "ifk_env.cuh"
 #include "ifk_solve_kernel.cuh"
 
 namespace ifk {
@@ -244,7 +245,7 @@ static StreamConfig choose_stream(const Geometry &g)
     if (smem > (size_t)kMaxSmemBytes || NVT == 0) return best;
     double best_cost = 1e30;
     int fcc = 0, fnv = 0;
-    if (const char *e = getenv("IFK_STREAM_CFG")) sscanf(e, "%d,%d", &fcc, &fnv);   // tuning only
+    fcc = env().stream_cfg[0]; fnv = env().stream_cfg[1];   // IFK_STREAM_CFG, tuning only
     static const int kCCs[] = {12, 8, 6, 4, 3, 2, 1};
     static const int kNVs[] = {3, 6, 8, 9, 12, 18, 24};
     static const int kCsizes[] = {1, 2, 4, 8};

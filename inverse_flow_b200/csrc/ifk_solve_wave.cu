@@ -1,0 +1,718 @@
+// Software-pipelined wavefront solve for the reference models' mid-sized layers ("wave" kernel).
+//
+// Same job as the resident kernel (ifk_solve_kernel.cuh) -- one launch instead of the reference's
+// (H+W-1)*C/4 launches + cudaDeviceSynchronize (inv_conv_with_bp_kernel_general.cu:72-129; adjoint
+// .cu:388-483) -- re-organised around what bounded that kernel on the B200 (profiles/r01_*):
+//
+//  * Fresh / old split.  Of the K-1 neighbour taps of pixel (h, w) on anti-diagonal d only (0,1)
+//    and (1,0) lie on diagonal d-1; all others are at least two diagonals old.  A thread therefore
+//    computes, inside step d, the OLD part of its row's NEXT pixel (diagonal d+1: everything it
+//    reads was visible at the barrier that opened step d) and carries it in registers; the
+//    dependent chain of a step shrinks to  barrier -> 2 shared loads -> a quarter of the FMAs ->
+//    shuffle reduce -> store,  and three quarters of the arithmetic fills its latency gaps.
+//  * T folded.  z = T x (T = (I + A0)^-1, tap 0 of the prepared kernel) is one more "old" tap that
+//    reads the input image instead of y: no pre-pass, no z buffer.  The image arrives NCHW by one
+//    TMA bulk copy, is transposed once into an NHWC buffer of the same geometry as y (one barrier),
+//    and the finished y leaves by coalesced stores straight from the NHWC buffer.
+//  * Everything compile-time (group width, taps, channel tile, reduction split, vector width, rows
+//    per thread): no index arithmetic, no constant-bank reads, no padding work in the loop.
+//  * NHWC buffers with an odd pixel stride (in vectors) and a row pad chosen on the host by
+//    enumerating the bank conflicts of the gather pattern (r01: 44 % conflict wavefronts).
+//
+// Thread -> (row slot, channel tile ct of CC outputs, reduction slice ks of NS); lanes of one pixel
+// = NCT*NS.  After the reduce-scatter over the NS lanes each finished channel sits on one lane,
+// which writes it.
+#include <map>
+#include <mutex>
+#include <stdio.h>
+#include <tuple>
+#include "ifk_env.cuh"
+#include "ifk_solve_kernel.cuh"
+
+namespace ifk {
+
+struct WaveParams {
+    const float *in;
+    float *out;
+    const float4 *pack;  // this direction's packed weights (wave_pack_kernel): [group][j][lane of the pixel]
+    const int *codes;    // [group-independent][slot][lane of the pixel]: tap / channel-vector code per entry
+    int B, C, H, W;
+    int nslots;         // image rows in flight (threads / lanes per pixel)
+    int flip;           // as SolveParams::flip
+    int bulk;           // TMA bulk copy of the input image possible (size / alignment)
+    int early;          // prepared weights may be fetched ahead of griddepcontrol.wait (ifk.h: IFK_FLAG_*)
+    int PS, RSP;        // pixel stride / row stride of the NHWC buffers, floats
+    int YN;             // floats per NHWC buffer
+    int XN;             // floats of the NCHW staging buffer
+    unsigned mW;        // ceil(2^32 / W): m / W == umulhi(m, mW) for every pixel index
+    int tm_shift;       // log2 of the pixel lanes of the transposing passes (a power of two dividing the threads)
+    long long *probe;   // clock64() stamps of CTA (0,0) thread 0 (ifk_inverse_probe_f32), or nullptr
+};
+
+// reduce-scatter of N per-lane partial sums over M adjacent lanes (compile-time recursive halving,
+// see Rs in ifk_solve_kernel.cuh): N/2 + N/4 + ... shuffles, log2(M) levels
+template <int N, int M>
+struct RsC {
+    __device__ __forceinline__ static void run(float *acc, int ks)
+    {
+        if constexpr (M > 1) {
+            constexpr int HALF = (N + 1) / 2;
+            const bool hi = (ks & (M / 2)) != 0;
+#pragma unroll
+            for (int i = 0; i < HALF; i++) {
+                const float lo_v = acc[i];
+                const float hi_v = (i + HALF < N) ? acc[i + HALF] : 0.f;
+                const float send = hi ? lo_v : hi_v;
+                const float keep = hi ? hi_v : lo_v;
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, M / 2);
+            }
+            RsC<HALF, M / 2>::run(acc, ks);
+        }
+    }
+};
+__host__ __device__ constexpr int rs_final(int n, int m) { return m > 1 ? rs_final((n + 1) / 2, m / 2) : n; }
+
+// predicated shared-memory store without a branch (a branch around the store splits the step's basic
+// block and with it ptxas' freedom to fill the shuffle latencies with the look-ahead FMAs)
+__device__ __forceinline__ void sts_f32_if(uint32_t addr, float v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}"
+                 ::"r"(addr), "f"(v), "r"((unsigned)pred) : "memory");
+}
+
+template <int CG, int KH, int KW, int CC, int NS, int VEC>
+struct WaveCfg {
+    static_assert(VEC == 2 || VEC == 4, "packed pairs need an even vector width");
+    static_assert(CG % VEC == 0 && CG % CC == 0, "tiles must divide the group");
+    static constexpr int K = KH * KW;
+    static constexpr int NCT = CG / CC;
+    static constexpr int LPP = NCT * NS;                       // lanes per pixel
+    static_assert((32 % NS) == 0, "the reduction split stays inside a warp");
+    static_assert((LPP % 32) == 0 || (32 % LPP) == 0, "pixels must not straddle warps unevenly");
+    static constexpr int CGV = CG / VEC;
+    static constexpr int NFT = (KW > 1 ? 1 : 0) + (KH > 1 ? 1 : 0);   // fresh taps: (0,1), (1,0)
+    static constexpr int NOT = K - 1 - NFT;                           // older y taps
+    static constexpr int NF = NFT * CGV;                               // fresh vector entries
+    static constexpr int NO = (NOT + 1) * CGV;                         // old entries: y taps + the T (input) tap
+    static constexpr int NVF = (NF + NS - 1) / NS;
+    static constexpr int NVO = (NO + NS - 1) / NS;
+    static constexpr int PF = NVF * VEC / 2, PO = NVO * VEC / 2;       // packed pairs per output channel
+    static constexpr int NW4 = (CC * (PF + PO) + 1) / 2;               // float4 of packed weights per thread
+    static constexpr int OWN = rs_final(CC, NS);                       // finished channels per lane (max)
+};
+
+// entry code (wave_pack_kernel writes them, the solve decodes them): which neighbour a vector entry reads
+__host__ __device__ inline int wave_code(int qh, int qw, int chan, bool is_x) { return qh | (qw << 8) | (chan << 16) | (is_x ? 1 << 30 : 0); }
+
+#define IFK_WPROBE(i) do { if (p.probe && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.probe[i] = clock64(); } while (0)
+
+template <int CG, int KH, int KW, int CC, int NS, int VEC, int ITERS, int NTHR>
+__global__ void __launch_bounds__(NTHR)
+solve_wave_kernel(const WaveParams p)
+{
+    typedef WaveCfg<CG, KH, KW, CC, NS, VEC> Cfg;
+    constexpr int LPP = Cfg::LPP, CGV = Cfg::CGV, NVF = Cfg::NVF, NVO = Cfg::NVO, PF = Cfg::PF, PO = Cfg::PO;
+    constexpr int OWN = Cfg::OWN, NW4 = Cfg::NW4;
+    IFK_WPROBE(0);
+    extern __shared__ __align__(128) float smem[];
+    const int H = p.H, W = p.W, HW = p.H * p.W, PS = p.PS, RSP = p.RSP;
+    const int tid = threadIdx.x, nthr = blockDim.x;             // nthr <= NTHR (small images need fewer rows)
+
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);         // 16 bytes reserved
+    float *xbuf = smem + 4;                                     // [CG][HW] the input image as it lies in memory
+    float *yb = xbuf + p.XN;                                    // [H+KH-1][..][PS] y, zero halo top / left
+    float *xh = yb + p.YN;                                      // same geometry: the input image, NHWC
+
+    const int G = blockIdx.y;
+    const uint32_t img_bytes = (uint32_t)(CG * HW) * 4u;
+    const size_t img_stride = (size_t)p.C * HW;
+    const float *in0 = p.in + (size_t)G * CG * HW;
+    float *out0 = p.out + (size_t)G * CG * HW;
+
+    const int l = tid % LPP, slot = tid / LPP;
+    const int ks = l % NS, ct = l / NS;
+    const bool worker = slot < p.nslots;
+
+    // this thread's slice of the prepared kernel -> registers: packed pairs along the reduction axis, laid
+    // out by wave_pack_kernel so that a warp reads consecutive 16-byte words (flat pair index i*CC + cc)
+    f32x2_t wreg[2 * NW4];
+    int offs[NVF + NVO];
+    const int xoff = p.YN * 4;                                  // xh lies YN floats behind yb
+    auto load_weights = [&]() {
+        const ulonglong2 *pk = reinterpret_cast<const ulonglong2 *>(p.pack) + (size_t)G * NW4 * LPP + l;
+#pragma unroll
+        for (int j = 0; j < NW4; j++) {
+            const ulonglong2 w4 = __ldg(pk + j * LPP);      // two packed pairs; nothing waits for them here
+            wreg[2 * j] = w4.x;
+            wreg[2 * j + 1] = w4.y;
+        }
+#pragma unroll
+        for (int j = 0; j < NVF + NVO; j++) {
+            const int code = __ldg(p.codes + j * LPP + l);
+            const int qh = code & 0xff, qw = (code >> 8) & 0xff, chan = (code >> 16) & 0x3fff;
+            offs[j] = ((-qh * RSP - qw * PS) + chan) * 4 + ((code >> 30) & 1) * xoff;
+        }
+    };
+
+    // Programmatic dependent launch.  The prepared weights may be fetched ahead of the dependency
+    // wait only when the caller vouches that the previous operation of the stream did not write them
+    // (IFK_FLAG_STABLE_PREPARED); the dependents are released AFTER the wait, so that "the kernel
+    // before my predecessor has completed and is visible" holds transitively for them.  Either way the
+    // weight fetch (one L2 round trip) is in flight while the image lands and is transposed: nothing
+    // below needs the weights before the wavefront starts.
+    if (p.early) load_weights();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    int b = blockIdx.x;
+    if (p.bulk && tid == 0) {
+        mbar_init(bar, 1);
+        if (b < p.B) {
+            mbar_expect_tx(bar, img_bytes);
+            bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
+        }
+        smem[2] = 0.f;          // source of the opaque zero used by Hold
+    }
+    if (!p.early) load_weights();
+    // zero halo (and the extra column the look-ahead touches): once per CTA -- the interior of xh is
+    // rewritten for every image, the interior of yb is written before it is read
+    for (int i = tid * 4; i < 2 * p.YN; i += nthr * 4)
+        *reinterpret_cast<float4 *>(yb + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();            // zero fill and mbarrier init visible
+    IFK_WPROBE(1);
+
+    // which of the tile's CC output channels this lane finishes after the reduce-scatter
+    int own_off, own_size;
+    rs_owner(CC, NS, ks, &own_off, &own_size);
+    if (!worker) own_size = 0;
+    Hold hold;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hold.zero) : "r"(smem_u32(smem + 2)) : "memory");
+    const uint32_t ybase = hold(smem_u32(yb) + (uint32_t)(((KH - 1) * RSP + (KW - 1) * PS) * 4));   // pixel (0, 0)
+    const uint32_t own_bytes = hold((uint32_t)(ct * CC + own_off) * 4u);
+    const uint32_t pix_step = hold((uint32_t)PS * 4u);                                   // per diagonal
+    const uint32_t pix_iter = hold((uint32_t)(p.nslots * (RSP - PS)) * 4u);              // per row iteration
+    const uint32_t pix0 = ybase + (uint32_t)(slot * (RSP - PS)) * 4u;                    // row `slot`, d = 0
+    const int ndiag = hold(H + W - 1);
+    const int Wr = hold(W), nsl = hold(p.nslots);
+    own_size = hold(own_size);
+    const int slot_r = hold(slot);
+    // memory index of solver pixel (h, w) = idx0 + sh*h*W + sw*w (reflected axes walk backwards)
+    const int sw = (p.flip & 1) ? -1 : 1, sh = (p.flip & 2) ? -1 : 1;
+    // the transposing passes: TM pixel lanes x TC channel lanes
+    const int TM = 1 << p.tm_shift, TC = nthr >> p.tm_shift;
+    const int tm = tid & (TM - 1), tc = tid >> p.tm_shift;
+    IFK_WPROBE(2);
+
+    uint32_t parity = 0;
+    for (; b < p.B; b += gridDim.x) {
+        const int b_next = b + gridDim.x;
+        IFK_WPROBE(3);
+        if (p.bulk) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            const float *src = in0 + (size_t)b * img_stride;
+            for (int i = tid; i < CG * HW; i += nthr) xbuf[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        IFK_WPROBE(4);
+        // transpose the image into xh.  Threads = TM pixel lanes x TC channel lanes (TM a power of two): a
+        // thread walks memory pixels m = tm, tm + TM, ... and, per pixel, channel vectors cv = tc, tc + TC, ...;
+        // consecutive lanes take consecutive pixels, so the loads are conflict free and -- with PS/VEC odd --
+        // so are the vector stores.  Loads of up to four vectors are issued before the first store.
+        for (int m = tm; m < HW; m += TM) {
+            const int hm = (int)__umulhi((unsigned)m, p.mW), wm = m - hm * W;
+            const int h = sh > 0 ? hm : H - 1 - hm, w = sw > 0 ? wm : W - 1 - wm;
+            float *d = xh + ((h + KH - 1) * RSP + (w + KW - 1) * PS) + tc * VEC;
+            const float *sp = xbuf + m + tc * VEC * HW;
+            const int dstep = TC * VEC, sstep = TC * VEC * HW;
+#pragma unroll 2
+            for (int cv = tc; cv < CGV; cv += TC, d += dstep, sp += sstep) {
+                if (VEC == 4) *reinterpret_cast<float4 *>(d) = make_float4(sp[0], sp[HW], sp[2 * HW], sp[3 * HW]);
+                else *reinterpret_cast<float2 *>(d) = make_float2(sp[0], sp[HW]);
+            }
+        }
+        __syncthreads();
+        if (p.bulk && tid == 0 && b_next < p.B) {                 // xbuf is free: prefetch the next image
+            mbar_expect_tx(bar, img_bytes);
+            bulk_load(xbuf, in0 + (size_t)b_next * img_stride, img_bytes, bar);
+        }
+        IFK_WPROBE(5);
+
+        // ---- wavefront ------------------------------------------------------------------------
+        f32x2_t acc[ITERS][CC];          // old part of the row's pixel on the coming diagonal
+        // old part (taps two or more diagonals back + T x) of the pixel at `pn`
+        auto old_part = [&](uint32_t pn, bool act_n, f32x2_t *a) {
+            const uint32_t pa = act_n ? pn : ybase;
+            f32x2_t v[PO];
+#pragma unroll
+            for (int j = 0; j < NVO; j++) lds_pairs<VEC>(v + j * (VEC / 2), pa + (uint32_t)offs[NVF + j]);
+#pragma unroll
+            for (int cc = 0; cc < CC; cc++) a[cc] = 0ull;
+#pragma unroll
+            for (int i = 0; i < PO; i++)
+#pragma unroll
+                for (int cc = 0; cc < CC; cc++) a[cc] = fma_f32x2(wreg[(PF + i) * CC + cc], v[i], a[cc]);
+        };
+        // one wavefront step of a row: the fresh part of its pixel on this diagonal (taps on the previous
+        // diagonal), reduction over the NS lanes, store -- and the old part of its next pixel, whose loads
+        // are issued up front and whose FMAs fill the latency of the reduction's shuffles
+        auto step = [&](uint32_t pix, bool act, bool act_n, f32x2_t *a) {
+            const uint32_t pa = act ? pix : ybase;
+            const uint32_t pn = act_n ? pix + pix_step : ybase;
+            f32x2_t vf[PF > 0 ? PF : 1], vo[PO];
+#pragma unroll
+            for (int j = 0; j < NVF; j++) lds_pairs<VEC>(vf + j * (VEC / 2), pa + (uint32_t)offs[j]);
+#pragma unroll
+            for (int j = 0; j < NVO; j++) lds_pairs<VEC>(vo + j * (VEC / 2), pn + (uint32_t)offs[NVF + j]);
+#pragma unroll
+            for (int i = 0; i < PF; i++)
+#pragma unroll
+                for (int cc = 0; cc < CC; cc++) a[cc] = fma_f32x2(wreg[i * CC + cc], vf[i], a[cc]);
+            float s[CC];
+#pragma unroll
+            for (int cc = 0; cc < CC; cc++) s[cc] = sum_f32x2(a[cc]);
+#pragma unroll
+            for (int cc = 0; cc < CC; cc++) a[cc] = 0ull;
+            // (consumed last-loaded-first: every accumulator's chain starts with the last vector, so ptxas has
+            //  to put all the loads in flight before the first look-ahead FMA instead of load/use pairs)
+#pragma unroll
+            for (int i = PO - 1; i >= 0; i--)
+#pragma unroll
+                for (int cc = 0; cc < CC; cc++) a[cc] = fma_f32x2(wreg[(PF + i) * CC + cc], vo[i], a[cc]);
+            RsC<CC, NS>::run(s, ks);
+#pragma unroll
+            for (int i = 0; i < OWN; i++) sts_f32_if(pa + own_bytes + 4u * i, s[i], act && i < own_size);
+        };
+
+        {   // diagonal 0's old part (only pixel (0,0) is live there; the others are discarded)
+            uint32_t pix = pix0;
+            int col = -slot_r;
+#pragma unroll
+            for (int it = 0; it < ITERS; it++, pix += pix_iter, col -= nsl) {
+                const bool row_ok = worker && slot_r + it * nsl < H;
+                old_part(pix, row_ok && (unsigned)col < (unsigned)Wr, acc[it]);
+            }
+        }
+        uint32_t pix_d = pix0;
+        for (int d = 0; d < ndiag; d++, pix_d += pix_step) {
+            if (d > 0) __syncthreads();             // diagonal d-1 is visible
+            uint32_t pix = pix_d;
+            int col = d - slot_r;
+#pragma unroll
+            for (int it = 0; it < ITERS; it++, pix += pix_iter, col -= nsl) {
+                const bool row_ok = worker && slot_r + it * nsl < H;
+                const bool act = row_ok && (unsigned)col < (unsigned)Wr;
+                const bool act_n = row_ok && (unsigned)(col + 1) < (unsigned)Wr;
+                if (!__any_sync(0xffffffffu, act || act_n)) continue;       // warp-uniform
+                step(pix, act, act_n, acc[it]);
+            }
+        }
+        IFK_WPROBE(6);
+        __syncthreads();
+
+        // ---- y leaves: NHWC shared memory -> NCHW global, coalesced (consecutive threads = consecutive
+        //      memory pixels of one channel vector; PS/VEC odd keeps the vector loads conflict free)
+        float *dst = out0 + (size_t)b * img_stride;
+        for (int m = tm; m < HW; m += TM) {
+            const int hm = (int)__umulhi((unsigned)m, p.mW), wm = m - hm * W;
+            const int h = sh > 0 ? hm : H - 1 - hm, w = sw > 0 ? wm : W - 1 - wm;
+            const float *sp = yb + ((h + KH - 1) * RSP + (w + KW - 1) * PS) + tc * VEC;
+            float *d = dst + m + tc * VEC * HW;
+            const int sstep = TC * VEC, dstep = TC * VEC * HW;
+#pragma unroll 2
+            for (int cv = tc; cv < CGV; cv += TC, sp += sstep, d += dstep) {
+                if (VEC == 4) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(sp);
+                    d[0] = t4.x; d[HW] = t4.y; d[2 * HW] = t4.z; d[3 * HW] = t4.w;
+                } else {
+                    const float2 t2 = *reinterpret_cast<const float2 *>(sp);
+                    d[0] = t2.x; d[HW] = t2.y;
+                }
+            }
+        }
+        IFK_WPROBE(7);
+        if (b_next < p.B) __syncthreads();          // yb is rewritten by the next image's wavefront
+    }
+    IFK_WPROBE(8);
+}
+
+// Packed weights for the wave kernel, built from the canonical prepared rows ([co][tap][ci], ifk_prepare.cu):
+// for lane l = (ct, ks) of a pixel the flat pair index f = i*CC + cc (i-th packed pair of the lane's reduction
+// slice, output channel ct*CC + cc) lands in float4 number f/2 -- stored [f/2][l], so that a warp's loads are
+// consecutive 16-byte words.  `codes` gets, once per direction-independent geometry, the neighbour each vector
+// entry of a lane reads.  One thread per (layer, dir, group, lane, pair).
+struct WavePackParams {
+    const float *prepared;   // canonical, [layer][dir][group][co][KDP]
+    float *pack;             // [layer][dir][group][NW4][LPP] float4
+    size_t pack_floats;      // floats of one layer's pack; its codes ([(NVF+NVO)][LPP] ints) follow
+    size_t prepared_stride, pack_stride;      // floats between layers (pack_stride: of the pack section)
+    int C, cg, kh, kw, cc, ns, vec, KDP, groups, count;
+};
+
+__global__ void __launch_bounds__(256)
+wave_pack_kernel(const WavePackParams q)
+{
+    const int K = q.kh * q.kw, cgv = q.cg / q.vec, nct = q.cg / q.cc, lpp = nct * q.ns;
+    const int nft = (q.kw > 1) + (q.kh > 1), not_ = K - 1 - nft;
+    const int NF = nft * cgv, NO = (not_ + 1) * cgv;
+    const int nvf = (NF + q.ns - 1) / q.ns, nvo = (NO + q.ns - 1) / q.ns;
+    const int pf = nvf * q.vec / 2, po = nvo * q.vec / 2;
+    const int npairs = q.cc * (pf + po), nw4 = (npairs + 1) / 2;
+    const long total = (long)q.count * 2 * q.groups * lpp * (2 * nw4);
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long r = e;
+        const int f = (int)(r % (2 * nw4)); r /= 2 * nw4;        // flat pair index (the pad pair of an odd count too)
+        const int l = (int)(r % lpp); r /= lpp;
+        const int G = (int)(r % q.groups); r /= q.groups;
+        const int dir = (int)(r % 2);
+        const int layer = (int)(r / 2);
+        const int ks = l % q.ns, ct = l / q.ns;
+        float w0 = 0.f, w1 = 0.f;
+        int code = 0, slot_j = -1;
+        if (f < npairs) {
+            const int i = f / q.cc, cc = f - i * q.cc;           // i-th packed pair of the slice
+            const bool fresh = i < pf;
+            const int ip = fresh ? i : i - pf;
+            const int j = ip / (q.vec / 2), e2 = ip - j * (q.vec / 2);      // vector entry slot, pair inside it
+            const int ent = j * q.ns + ks;
+            const bool valid = ent < (fresh ? NF : NO);
+            if (valid) {
+                const int ti = ent / cgv, qv = ent - ti * cgv;
+                int t = 0;
+                bool is_x = false;
+                if (fresh) t = (q.kw > 1 && ti == 0) ? 1 : q.kw;
+                else if (ti == not_) is_x = true;
+                else {
+                    int n = 0;
+                    for (int tt = 1; tt < K; tt++) {
+                        if (tt / q.kw + tt % q.kw < 2) continue;
+                        if (n == ti) { t = tt; break; }
+                        n++;
+                    }
+                }
+                const float *src = q.prepared + (size_t)layer * q.prepared_stride +
+                                   ((size_t)dir * q.C + (size_t)G * q.cg + ct * q.cc + cc) * q.KDP + t * q.cg +
+                                   qv * q.vec + 2 * e2;
+                w0 = src[0];
+                w1 = src[1];
+                code = wave_code(t / q.kw, t % q.kw, qv * q.vec, is_x);
+                if (cc == 0 && e2 == 0 && dir == 0 && G == 0) slot_j = (fresh ? 0 : nvf) + j;
+            } else if (cc == 0 && e2 == 0 && dir == 0 && G == 0) {
+                slot_j = (fresh ? 0 : nvf) + j;                 // padding entry: offset 0, zero weights
+            }
+        }
+        float *dstp = q.pack + (size_t)layer * q.pack_stride + (((size_t)dir * q.groups + G) * nw4 + f / 2) * lpp * 4 +
+                      (size_t)l * 4 + (f & 1) * 2;
+        dstp[0] = w0;
+        dstp[1] = w1;
+        if (slot_j >= 0)
+            reinterpret_cast<int *>(q.pack + (size_t)layer * q.pack_stride + q.pack_floats)[(size_t)slot_j * lpp + l] = code;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+// X(CG, KH, KW, CC, NS, VEC, ITERS, NTHR)
+#define IFK_WAVE_VARIANTS                                                                           \
+    X(12, 3, 3, 6, 4, 2, 1, 128) X(12, 3, 3, 6, 4, 2, 2, 128) X(12, 3, 3, 6, 4, 2, 4, 128)           \
+    X(12, 3, 3, 6, 8, 2, 1, 256) X(12, 3, 3, 6, 8, 2, 2, 256)                                        \
+    X(24, 3, 3, 6, 8, 2, 1, 256) X(24, 3, 3, 6, 8, 2, 2, 256)                                        \
+    X(24, 3, 3, 6, 16, 2, 2, 256) X(24, 3, 3, 6, 16, 2, 4, 256)                                      \
+    X(48, 3, 3, 6, 16, 2, 2, 256)                                                                    \
+    X(48, 3, 3, 6, 32, 2, 4, 256)                                                                    \
+    X(6, 3, 3, 6, 4, 2, 1, 256) X(6, 3, 3, 6, 4, 2, 2, 256)
+
+struct WaveVariant {
+    int cg, kh, kw, cc, ns, vec, iters, nthr;
+};
+static const WaveVariant kWaveVariants[] = {
+#define X(CG, KHc, KWc, CC, NS, VEC, IT, NT) {CG, KHc, KWc, CC, NS, VEC, IT, NT},
+    IFK_WAVE_VARIANTS
+#undef X
+};
+
+struct WaveConfig {
+    bool ok;
+    WaveVariant v;
+    int nslots, threads, PS, RSP, YN, XN, grid_x;
+    size_t smem_bytes;
+    double conflict;      // modelled shared-memory wavefronts per ideal wavefront of the gather (1.0 = none)
+};
+
+// Shared-memory wavefronts of one wavefront step's gathers for a (PS, RSP) layout: every load
+// instruction is replayed per phase (8 lanes for 128-bit, 16 for 64-bit accesses) as many times as
+// the most loaded bank has distinct words.  All rows live, mid-image diagonal.
+static double wave_gather_cost(const WaveVariant &v, int H, int W, int nslots, int threads, int PS, int RSP)
+{
+    const int nct = v.cg / v.cc, lpp = nct * v.ns, cgv = v.cg / v.vec, K = v.kh * v.kw;
+    const int nft = (v.kw > 1) + (v.kh > 1), not_ = K - 1 - nft;
+    const int NF = nft * cgv, NO = (not_ + 1) * cgv;
+    const int nvf = (NF + v.ns - 1) / v.ns, nvo = (NO + v.ns - 1) / v.ns;
+    const int phase = v.vec == 4 ? 8 : 16;
+    const int YN = (H + v.kh - 1) * RSP;
+    long total = 0, ideal = 0;
+    const int d = (H + W) / 2;
+    for (int w0 = 0; w0 < threads; w0 += 32) {
+        for (int j = 0; j < nvf + nvo; j++) {
+            const bool fresh = j < nvf;
+            for (int ph = 0; ph < 32; ph += phase) {
+                int words[32][4];
+                int nw = 0, bankcnt[32] = {0};
+                for (int ln = ph; ln < ph + phase; ln++) {
+                    const int tid = w0 + ln;
+                    const int l = tid % lpp, slot = tid / lpp, ks = l % v.ns;
+                    int row = slot, col = d - slot;
+                    if (slot >= nslots || row >= H || col < 0 || col >= W) { row = 0; col = 0; }
+                    if (!fresh) col += 1;
+                    const int e = (fresh ? j : j - nvf) * v.ns + ks;
+                    int off = 0;
+                    if (fresh) {
+                        if (e < NF) {
+                            const int ft = e / cgv, q = e % cgv;
+                            const int t = (v.kw > 1 && ft == 0) ? 1 : v.kw;
+                            off = -(t / v.kw) * RSP - (t % v.kw) * PS + q * v.vec;
+                        }
+                    } else if (e < NO) {
+                        const int oi = e / cgv, q = e % cgv;
+                        int t = 0;
+                        if (oi < not_) {
+                            int n = 0;
+                            for (int tt = 1; tt < K; tt++) {
+                                if (tt / v.kw + tt % v.kw < 2) continue;
+                                if (n == oi) { t = tt; break; }
+                                n++;
+                            }
+                        }
+                        off = -(t / v.kw) * RSP - (t % v.kw) * PS + q * v.vec + (oi == not_ ? YN : 0);
+                    }
+                    const int base = (row + v.kh - 1) * RSP + (col + v.kw - 1) * PS + off;
+                    for (int e2 = 0; e2 < v.vec; e2++) {
+                        const int word = base + e2;
+                        bool seen = false;
+                        for (int k = 0; k < nw; k++) seen |= words[k / 4][k % 4] == word;
+                        if (!seen && nw < 128) {
+                            words[nw / 4][nw % 4] = word;
+                            nw++;
+                            bankcnt[((word % 32) + 32) % 32]++;
+                        }
+                    }
+                }
+                int worst = 1;
+                for (int bk = 0; bk < 32; bk++) worst = bankcnt[bk] > worst ? bankcnt[bk] : worst;
+                total += worst;
+                ideal += 1;
+            }
+        }
+    }
+    return ideal ? (double)total / ideal : 1.0;
+}
+
+// (cc, ns, vec) family serving a (Cg, KH, KW): fixes the packed-weight layout, so it must not depend on
+// the image size or the batch -- every variant of one (Cg, KH, KW) in the table shares it
+static const WaveVariant *wave_family(const Geometry &g)
+{
+    const EnvKnobs &k = env();
+    for (const WaveVariant &v : kWaveVariants) {
+        if (v.cg != g.Cg || v.kh != g.KH || v.kw != g.KW) continue;
+        if (k.wave_cfg[0] && (k.wave_cfg[0] != v.cc || k.wave_cfg[1] != v.ns || k.wave_cfg[2] != v.vec)) continue;
+        return &v;
+    }
+    return nullptr;
+}
+
+static WaveConfig choose_wave_uncached(const Geometry &g)
+{
+    WaveConfig c{};
+    c.ok = false;
+    const EnvKnobs &k = env();
+    if (k.wave_off || k.pins_other_solver()) return c;
+    const int max_smem = device_max_smem_optin();
+    const WaveVariant *fam = wave_family(g);
+    if (!fam) return c;
+    for (const WaveVariant &v : kWaveVariants) {
+        if (v.cg != g.Cg || v.kh != g.KH || v.kw != g.KW) continue;
+        if (g.W < 2 || g.H * g.W < 2) continue;               // the index divisions use 32-bit magic multipliers
+        if (v.cc != fam->cc || v.ns != fam->ns || v.vec != fam->vec) continue;
+        const int lpp = (v.cg / v.cc) * v.ns;
+        int nslots = v.nthr / lpp;
+        if (nslots < 1) continue;
+        if (nslots > g.H) nslots = g.H;
+        if (nslots * v.iters < g.H) continue;                 // rows per thread of this variant do not cover H
+        const int threads = round_up(nslots * lpp, 32);
+        // layout: odd pixel stride in vector units; row pad by enumeration of the gather's bank conflicts
+        int PS = round_up(g.Cg, v.vec);
+        if (((PS / v.vec) & 1) == 0) PS += v.vec;
+        const int row_px = g.W + g.KW;                        // halo left + one look-ahead column right
+        int best_pad = 0;
+        double best_cost = 1e30;
+        for (int pad = 0; pad < 32; pad += v.vec) {
+            const double cost = wave_gather_cost(v, g.H, g.W, nslots, threads, PS, row_px * PS + pad);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best_pad = pad; }
+        }
+        const int RSP = row_px * PS + best_pad;
+        const int YN = round_up((g.H + g.KH - 1) * RSP, 4);
+        const int XN = round_up(g.Cg * g.H * g.W, 4);
+        const size_t smem = 16 + ((size_t)XN + 2 * (size_t)YN) * sizeof(float);
+        if (smem > (size_t)max_smem) continue;
+        c.ok = true;
+        c.v = v; c.nslots = nslots; c.threads = threads; c.PS = PS; c.RSP = RSP; c.YN = YN; c.XN = XN;
+        c.smem_bytes = smem; c.conflict = best_cost;
+        break;                                                // variants are listed by rising rows per thread
+    }
+    if (!c.ok) return c;
+    // one CTA per SM is all the register file holds; a stripe of images per CTA beyond that
+    int grid_x = (device_sm_count() + g.groups - 1) / g.groups;
+    if (grid_x > g.B) grid_x = g.B;
+    if (grid_x < 1) grid_x = 1;
+    c.grid_x = grid_x;
+    return c;
+}
+
+static WaveConfig choose_wave(const Geometry &g)
+{
+    // memoised per geometry (the enumeration above costs tens of microseconds; a launch must not)
+    typedef std::tuple<int, int, int, int, int, int, int> Key;
+    static std::map<Key, WaveConfig> cache;
+    static std::mutex mu;
+    static const EnvKnobs *seen = nullptr;
+    static EnvKnobs seen_copy;
+    const EnvKnobs &k = env();
+    const Key key(g.C, g.H, g.W, g.KH, g.KW, g.groups, g.B < device_sm_count() ? g.B : device_sm_count());
+    std::lock_guard<std::mutex> lock(mu);
+    if (!seen || memcmp(&seen_copy, &k, sizeof(EnvKnobs)) != 0) {     // knobs reloaded (tests): start over
+        cache.clear();
+        seen_copy = k;
+        seen = &k;
+    }
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const WaveConfig c = choose_wave_uncached(g);
+    cache[key] = c;
+    return c;
+}
+
+bool wave_solve_available(const Geometry &g) { return choose_wave(g).ok; }
+
+int describe_wave_solve(const Geometry &g, char *buf, size_t buflen)
+{
+    const WaveConfig c = choose_wave(g);
+    snprintf(buf, buflen, "wave<cg=%d,k=%dx%d,cc=%d,ns=%d,vec=%d,iters=%d> slots=%d threads=%d ps=%d rsp=%d conflict=%.2f "
+             "smem=%zuB grid=%dx%d", c.v.cg, c.v.kh, c.v.kw, c.v.cc, c.v.ns, c.v.vec, c.v.iters, c.nslots, c.threads,
+             c.PS, c.RSP, c.conflict, c.smem_bytes, c.grid_x, g.groups);
+    return 0;
+}
+
+struct WavePackDims {
+    int lpp, nvf, nvo, nw4;
+    size_t pack_floats, code_ints;      // per layer: both directions / all groups; codes once
+};
+static WavePackDims wave_pack_dims(const WaveVariant &v, int groups)
+{
+    WavePackDims d{};
+    const int K = v.kh * v.kw, cgv = v.cg / v.vec, nct = v.cg / v.cc;
+    const int nft = (v.kw > 1) + (v.kh > 1), not_ = K - 1 - nft;
+    d.lpp = nct * v.ns;
+    d.nvf = (nft * cgv + v.ns - 1) / v.ns;
+    d.nvo = ((not_ + 1) * cgv + v.ns - 1) / v.ns;
+    d.nw4 = (v.cc * (d.nvf + d.nvo) * v.vec / 2 + 1) / 2;
+    d.pack_floats = (size_t)2 * groups * d.nw4 * d.lpp * 4;
+    d.code_ints = (size_t)round_up((d.nvf + d.nvo) * d.lpp, 4);
+    return d;
+}
+
+size_t prepared_floats(const Geometry &g)
+{
+    size_t n = (size_t)2 * g.C * g.KDP;                       // canonical rows, both directions
+    if (const WaveVariant *v = wave_family(g)) {
+        const WavePackDims d = wave_pack_dims(*v, g.groups);
+        n += d.pack_floats + d.code_ints;
+    }
+    return n;
+}
+
+int launch_wave_pack(const Geometry &g, float *prepared, int count, size_t prepared_stride, cudaStream_t s)
+{
+    const WaveVariant *v = wave_family(g);
+    if (!v || count <= 0) return 0;
+    const WavePackDims d = wave_pack_dims(*v, g.groups);
+    WavePackParams q{};
+    q.prepared = prepared;
+    q.pack = prepared + (size_t)2 * g.C * g.KDP;
+    q.pack_floats = d.pack_floats;
+    q.prepared_stride = prepared_stride;
+    q.pack_stride = prepared_stride;
+    q.C = g.C; q.cg = v->cg; q.kh = v->kh; q.kw = v->kw; q.cc = v->cc; q.ns = v->ns; q.vec = v->vec;
+    q.KDP = g.KDP; q.groups = g.groups; q.count = count;
+    const long total = (long)count * 2 * g.groups * d.lpp * (2 * d.nw4);
+    long blocks = (total + 255) / 256;
+    if (blocks > 8L * device_sm_count()) blocks = 8L * device_sm_count();
+    wave_pack_kernel<<<(unsigned)blocks, 256, 0, s>>>(q);
+    return cuda_status(cudaGetLastError());
+}
+
+int launch_solve_wave(const Geometry &g, const float *in, const float *prepared, float *out, bool reverse,
+                      int flags, long long *probe, cudaStream_t s)
+{
+    const WaveConfig c = choose_wave(g);
+    if (!c.ok) return IFK_ERR_UNSUPPORTED;
+    const WavePackDims d = wave_pack_dims(c.v, g.groups);
+    const float *pack = prepared + (size_t)2 * g.C * g.KDP;
+    WaveParams p{};
+    p.in = in; p.out = out;
+    p.pack = reinterpret_cast<const float4 *>(pack + (reverse ? d.pack_floats / 2 : 0));
+    p.codes = reinterpret_cast<const int *>(pack + d.pack_floats);
+    p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W;
+    p.nslots = c.nslots;
+    p.flip = reverse ? (g.orient ^ 3) : g.orient;
+    const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
+    p.bulk = (img_bytes % 16 == 0) && ((uintptr_t)in % 16 == 0) && !env().nobulk ? 1 : 0;
+    p.early = (flags & IFK_FLAG_STABLE_PREPARED) ? 1 : 0;
+    p.PS = c.PS; p.RSP = c.RSP; p.YN = c.YN; p.XN = c.XN;
+    p.mW = (unsigned)((0x100000000ULL + (unsigned)g.W - 1) / (unsigned)g.W);
+    {   // pixel lanes: the largest power of two <= H*W that divides the thread count
+        int sh = 0;
+        while ((2 << sh) <= g.H * g.W && c.threads % (2 << sh) == 0) sh++;
+        p.tm_shift = sh;
+    }
+    p.probe = probe;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(c.threads);
+    cfg.dynamicSmemBytes = c.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL, see the kernel prologue
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = env().pdl ? 1 : 0;
+#define X(CG, KHc, KWc, CC, NS, VEC, IT, NT)                                                          \
+    if (c.v.cg == CG && c.v.kh == KHc && c.v.kw == KWc && c.v.cc == CC && c.v.ns == NS && c.v.vec == VEC && \
+        c.v.iters == IT && c.v.nthr == NT) {                                                          \
+        auto kern = solve_wave_kernel<CG, KHc, KWc, CC, NS, VEC, IT, NT>;                             \
+        if (c.smem_bytes > 48 * 1024) {                                                               \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                                 (int)c.smem_bytes);                                  \
+            if (e != cudaSuccess) return (int)e;                                                      \
+        }                                                                                             \
+        /* CTAs that fit one SM at once (registers, shared memory): a batch beyond the SM count runs that */ \
+        /* many images per SM concurrently, whose latency-bound wavefronts interleave */               \
+        int occ = 1;                                                                                  \
+        if (g.B * g.groups > device_sm_count() &&                                                     \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, c.smem_bytes) != cudaSuccess) \
+            occ = 1;                                                                                  \
+        if (occ < 1) occ = 1;                                                                         \
+        int gx = (device_sm_count() * occ + g.groups - 1) / g.groups;                                 \
+        if (gx > g.B) gx = g.B;                                                                       \
+        cfg.gridDim = dim3(gx < 1 ? 1 : gx, g.groups);                                                \
+        return cuda_status(cudaLaunchKernelEx(&cfg, kern, p));                                        \
+    }
+    IFK_WAVE_VARIANTS
+#undef X
+    return IFK_ERR_UNSUPPORTED;
+}
+
+int launch_solve_chain(const Geometry &g, int n, const int *orients, const float *const *prepared, const float *x,
+                       float *const *ys, cudaStream_t s)
+{
+    return IFK_ERR_UNSUPPORTED;
+}
+
+}  // namespace ifk

@@ -33,6 +33,7 @@
 // (inv_conv_with_bp_kernel_general.cu:72-129).
 #include <stdio.h>
 #include <stdlib.h>
+#include "ifk_env.cuh"
 #include "ifk_solve_kernel.cuh"
 
 namespace ifk {
@@ -412,7 +413,7 @@ static WindowConfig choose_window(const Geometry &g)
     if (smem > (size_t)kMaxSmemBytes) return best;
     double best_cost = 1e30;
     int fcc = 0, fnv = 0, fcs = 0, frp = 0;
-    if (const char *e = getenv("IFK_WINDOW_CFG")) sscanf(e, "%d,%d,%d,%d", &fcc, &fnv, &fcs, &frp);   // tuning only
+    fcc = env().window_cfg[0]; fnv = env().window_cfg[1]; fcs = env().window_cfg[2]; frp = env().window_cfg[3];   // IFK_WINDOW_CFG, tuning only
     static const int kCCs[] = {12, 8, 6, 4, 3, 2, 1};
     static const int kNVs[] = {3, 5, 6, 8, 9, 12, 18, 24};
     static const int kCsizes[] = {1, 2, 4, 8, 16};

@@ -54,6 +54,9 @@ class InvConvStack:
             st.C, st.H, st.W, st.k, st.n = C, H, W, k, n
             st.groups = default_groups(C) if groups is None else groups
             st.problem = _native.problem(self.batch, C, H, W, k, k, C, st.groups)
+            # every solve but the one right behind the stage's prepare may fetch its weights ahead of the
+            # programmatic-launch wait (ifk.h: IFK_FLAG_STABLE_PREPARED)
+            st.problem_stable = _native.with_flags(st.problem, _native.FLAG_STABLE_PREPARED)
             pf = self.lib.ifk_prepared_floats(ctypes.byref(st.problem))
             ws = self.lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(st.problem))
             if pf == 0:
@@ -94,8 +97,9 @@ class InvConvStack:
         p = ctypes.byref(st.problem)
         _native.check(lib.ifk_prepare_many_f32(p, st.n, st.w_base.data_ptr(), st.w_stride,
                                                st.prepared_all.data_ptr(), st.pf, s))
+        ps = ctypes.byref(st.problem_stable)
         for i in range(st.n):
-            _native.check(lib.ifk_inverse_f32(p, st.act[i].data_ptr(), st.prepared[i].data_ptr(),
+            _native.check(lib.ifk_inverse_f32(p if i == 0 else ps, st.act[i].data_ptr(), st.prepared[i].data_ptr(),
                                               st.act[i + 1].data_ptr(), s))
 
     def backward_stage(self, st):
@@ -104,10 +108,11 @@ class InvConvStack:
         main = torch.cuda.current_stream(self.device)
         s = ctypes.c_void_p(main.cuda_stream)
         p = ctypes.byref(st.problem)
+        ps = ctypes.byref(st.problem_stable)      # the prepares ran in the forward pass, long before
         g = st.grad_in
         for i in reversed(range(st.n)):
             dx = st.dxs[i]
-            _native.check(lib.ifk_bwd_input_f32(p, g.data_ptr(), st.prepared[i].data_ptr(), dx.data_ptr(), s))
+            _native.check(lib.ifk_bwd_input_f32(ps, g.data_ptr(), st.prepared[i].data_ptr(), dx.data_ptr(), s))
             side = self.sides[self._side_rr % len(self.sides)]
             self._side_rr += 1
             side.wait_stream(main)                            # fork: dW stage 1 needs this dX

@@ -189,10 +189,26 @@ def dense_L(w, H, W, groups=1):
 
 
 def max_rel_err(a, ref):
-    """max |a - ref| / max |ref|: the parity metric used throughout tests/ and bench.py."""
+    """max |a - ref| / max |ref|: the parity metric used throughout tests/ and bench.py.  A MAX-NORM relative
+    error (one denominator for the whole tensor), not an elementwise one -- see max_elem_rel_err."""
     a = np.asarray(a, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     den = float(np.max(np.abs(ref))) if ref.size else 0.0
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - ref))) / (den if den > 0 else 1.0)
+
+
+def max_elem_rel_err(a, ref, floor=1e-3):
+    """elementwise relative error max |a_i - ref_i| / |ref_i| over the entries with |ref_i| >= floor * max|ref|
+    (entries below the floor are covered by the max-norm metric only: their relative error is dominated by
+    the float32 rounding of terms far larger than they are)."""
+    a = np.asarray(a, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    den = float(np.max(np.abs(ref)))
+    if den == 0.0:
+        return float(np.max(np.abs(a)))
+    big = np.abs(ref) >= floor * den
+    return float(np.max(np.abs(a[big] - ref[big]) / np.abs(ref[big])))

@@ -43,3 +43,35 @@ def make_weight(rng, C, Cw, KH, KW, scale=0.05, dtype=np.float32):
         w[c, c, KH - 1, KW - 1] += 1.0
     w[:, -1, -1, -1] = 1.0
     return w.astype(dtype)
+
+
+class _KnobPatch:
+    """monkeypatch whose setenv / delenv of IFK_* knobs also tells the library to re-read them: the
+    library parses its environment once and caches it (include/ifk.h, ifk_debug_reload_env)."""
+
+    def __init__(self, inner):
+        self._inner = inner
+
+    def _reload(self, name):
+        if name.startswith("IFK_"):
+            from inverse_flow_b200 import _native
+            _native.reload_env()
+
+    def setenv(self, name, value, *a, **k):
+        self._inner.setenv(name, value, *a, **k)
+        self._reload(name)
+
+    def delenv(self, name, *a, **k):
+        self._inner.delenv(name, *a, **k)
+        self._reload(name)
+
+    def __getattr__(self, attr):
+        return getattr(self._inner, attr)
+
+
+@pytest.fixture
+def monkeypatch(monkeypatch):
+    patch = _KnobPatch(monkeypatch)
+    yield patch
+    monkeypatch.undo()
+    patch._reload("IFK_")

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_version_and_status_strings(lib):
-    assert lib.ifk_version() == 200
+    assert lib.ifk_version() == 300
     assert lib.ifk_status_string(0) == b"ok"
     for code in (-1, -2, -3, -4, -5, -6):
         assert lib.ifk_status_string(code) not in (b"ok", b"unknown ifk status")
@@ -65,9 +65,12 @@ def test_bad_geometry_is_rejected_before_any_launch(lib, kwargs, code):
 
 
 def test_problem_struct_matches_the_header():
-    """ifk_problem is nine ints, `orient` last (include/ifk.h); names map to IFK_ORIENT_*"""
-    assert ctypes.sizeof(_native.Problem) == 9 * ctypes.sizeof(ctypes.c_int)
-    assert [f[0] for f in _native.Problem._fields_][-1] == "orient"
+    """ifk_problem is ten ints, `orient` then `flags` last (include/ifk.h); names map to IFK_ORIENT_*"""
+    assert ctypes.sizeof(_native.Problem) == 10 * ctypes.sizeof(ctypes.c_int)
+    assert [f[0] for f in _native.Problem._fields_][-2:] == ["orient", "flags"]
+    header = open(os.path.join(ROOT, "include", "ifk.h")).read()
+    struct = header[header.index("typedef struct ifk_problem"):header.index("} ifk_problem;")]
+    assert re.findall(r"int ([A-Za-z, ]+);", struct) == ["B, C, H, W", "KH, KW", "Cw", "groups", "orient", "flags"]
     assert [_native.problem(1, 4, 5, 5, 3, 3, 4, 1, o).orient for o in ("TL", "TR", "BL", "BR")] == [0, 1, 2, 3]
     with pytest.raises(ValueError):
         _native.problem(1, 4, 5, 5, 3, 3, 4, 1, "XX")
@@ -94,7 +97,7 @@ def test_describe_solve_picks_the_on_chip_kernels_for_model_shapes(lib, monkeypa
     """model shapes stay on chip: the register/shuffle kernel where one warp's lanes cover the rows
     and a lane can hold its weights (MNIST-sized layers), the shared-memory resident kernel otherwise"""
     for shape, kind in [((100, 4, 14, 14, 2), "shfl<"), ((100, 8, 7, 7, 2), "shfl<"), ((64, 1, 28, 28, 3), "shfl<"),
-                        ((100, 12, 16, 16, 3), "smem<"), ((100, 24, 8, 8, 3), "smem<"), ((100, 48, 4, 4, 3), "smem<")]:
+                        ((100, 12, 16, 16, 3), "wave<"), ((100, 24, 8, 8, 3), "wave<"), ((100, 48, 4, 4, 3), "wave<")]:
         B, C, H, W, k = shape
         d = _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1))
         assert d.startswith(kind), (shape, d)
@@ -156,7 +159,7 @@ def test_kernel_selection_is_well_formed_over_the_sweep_grid(lib):
                         d = _native.describe_solve(p)
                         kind = d.split("<")[0].split(" ")[0]
                         kinds[kind] = kinds.get(kind, 0) + 1
-                        assert kind in ("shfl", "smem", "window", "stream", "global"), d
+                        assert kind in ("shfl", "wave", "smem", "window", "stream", "global"), d
                         m = re.search(r"smem=(\d+)B", d)
                         if m:
                             assert int(m.group(1)) <= 227 * 1024, d
@@ -171,4 +174,4 @@ def test_kernel_selection_is_well_formed_over_the_sweep_grid(lib):
                         assert lib.ifk_prepared_floats(ctypes.byref(p)) > 0
                         assert lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(p)) > 0
     # the grid exercises every solve kernel
-    assert set(kinds) == {"shfl", "smem", "window", "stream", "global"}, kinds
+    assert set(kinds) == {"shfl", "wave", "smem", "window", "stream", "global"}, kinds
