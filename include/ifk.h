@@ -183,6 +183,20 @@ int ifk_inverse_chain_f32(const ifk_problem *p, int n, const int *orients, const
 int ifk_inverse_probe_f32(const ifk_problem *p, const float *x, const float *prepared, float *y,
                           long long *probe, ifk_stream_t stream);
 
+/* ---- data-parallel gradient exchange ---------------------------------------------
+ * out[i] = sum over ranks r = 0..world-1 of buckets[r][i], summed in rank order on every rank (bit-identical
+ * results everywhere), as ONE kernel over peer memory: it hand-shakes with the other ranks, reads their
+ * buckets through NVLink/NVSwitch peer mappings and hand-shakes again before anyone may overwrite a bucket.
+ * Replaces the gradient reduction of the reference's nn.DataParallel (inf/if_multiGPU_imagenet32.py:410-411).
+ *   buckets[r] : rank r's bucket (n floats, 16-byte aligned) as mapped into THIS process (buckets[rank] = own)
+ *   flags[r]   : rank r's flag block, ifk_allreduce_flag_bytes() bytes, zeroed once before the first call
+ *   out        : local result, n floats, 16-byte aligned, not aliasing any bucket
+ * Every rank must call it with the same n, the same number of times and in the same order; one process per
+ * GPU (kernels of different ranks must be able to run at the same time).  Graph-capturable. */
+size_t ifk_allreduce_flag_bytes(void);
+int ifk_allreduce_peer_f32(const float *const *buckets, unsigned *const *flags, int rank, int world, float *out,
+                           size_t n, ifk_stream_t stream);
+
 /* Measured denominators for the roofline (bench.py, tools/hw_microbench.py).  Both calls synchronise the
  * device and are measuring aids, not part of the product path.
  *   ifk_debug_fp32_peak: TFLOP/s of independent FP32 FMAs on all SMs -- out_tflops[0] scalar FFMA,

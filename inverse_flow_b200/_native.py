@@ -21,6 +21,7 @@ EXPORTS = (
     "ifk_bwd_weight_f32", "ifk_bwd_weight_partial_f32", "ifk_bwd_weight_reduce_many_f32",
     "ifk_backward_f32", "ifk_describe_solve", "ifk_inverse_once_f32", "ifk_inverse_chain_f32",
     "ifk_inverse_probe_f32", "ifk_debug_reload_env", "ifk_debug_fp32_peak", "ifk_debug_latencies",
+    "ifk_allreduce_flag_bytes", "ifk_allreduce_peer_f32",
 )
 
 FLAG_STABLE_PREPARED = 1        # enum ifk_flags
@@ -77,6 +78,10 @@ def load():
     lib.ifk_inverse_probe_f32.argtypes = [P, vp, vp, vp, vp, vp]
     lib.ifk_debug_reload_env.restype = None
     lib.ifk_debug_reload_env.argtypes = []
+    lib.ifk_allreduce_flag_bytes.restype = sz
+    lib.ifk_allreduce_flag_bytes.argtypes = []
+    lib.ifk_allreduce_peer_f32.restype = ci
+    lib.ifk_allreduce_peer_f32.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, vp, sz, vp]
     lib.ifk_debug_fp32_peak.restype = ci
     lib.ifk_debug_fp32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.ifk_debug_latencies.restype = ci

@@ -69,10 +69,12 @@ static BwdWeightPlan make_plan(const Geometry &g)
     return pl;
 }
 
+// batch chunks (== partial buffers) of the stage-1 kernel that serves this geometry
+static int stage1_chunks(const Geometry &g);
+
 size_t bwd_weight_workspace_bytes(const Geometry &g)
 {
-    const BwdWeightPlan pl = make_plan(g);
-    return (size_t)pl.nchunks * g.C * g.Cg * g.K * sizeof(float);
+    return (size_t)stage1_chunks(g) * g.C * g.Cg * g.K * sizeof(float);
 }
 
 struct BwdWeightParams {
@@ -274,6 +276,211 @@ bwd_weight_partial_kernel(const BwdWeightParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage 1 for the reference models' layers ("quad" kernel): tiles that span ALL taps, 4 pixels per lane.
+//
+// The kernel above re-reads dX and y from shared memory once per tap (one work item per tap) and loads
+// TC + TK scalars per TC*TK FMAs.  Here a warp owns a tile of TC dX channels x TKC y channels x all K taps
+// (72 accumulators for 4 x 2 x 9) and a lane a QUAD of four horizontally adjacent pixels: dX arrives as one
+// 128-bit load per channel, the y neighbourhood of the quad as two 128-bit loads per (channel, tap row) --
+// an 8-wide window from which every horizontal tap is a register offset -- so one quad costs
+// TC + 2*TKC*KH vector loads for 4*TC*TKC*K FMAs (16 : 288).  Lanes stride over the (image, quad) pairs of
+// the CTA's batch chunk, which is staged once by TMA bulk copies (no re-staging per tap); one recursive-
+// halving reduction per tile at the end.  Grid = (batch chunks, groups, tile groups), sized to about a
+// third of the SMs: with 256 threads of ~170 registers a CTA cannot share an SM with a wavefront-solve CTA,
+// so in the backward pass these kernels live on the SMs the 100-image solves leave idle.
+// ------------------------------------------------------------------------------------------------
+struct QuadPlan {
+    bool ok;
+    int tiles, nz, tpw, nwarps, nchunks, per_chunk, XN;
+    size_t smem_bytes;
+};
+constexpr int kQuadTC = 4, kQuadTKC = 2, kQuadMaxWarps = 12;       // 384 threads: up to 168 registers each
+
+static QuadPlan make_quad_plan(const Geometry &g)
+{
+    QuadPlan q{};
+    q.ok = false;
+    if (g.KH != 3 || g.KW != 3 || g.W % 4 != 0 || g.Cg % kQuadTC != 0 || g.Cg % kQuadTKC != 0 || g.Cg < 12 || g.B < 1)
+        return q;
+    q.tiles = (g.Cg / kQuadTC) * (g.Cg / kQuadTKC);
+    // warps per CTA x tiles per warp: the combination that leaves the fewest idle tile slots
+    q.tpw = 2;
+    {
+        int best_waste = 1 << 30;
+        for (int nw : {12, 9, 8}) {
+            const int nz = (q.tiles + nw * q.tpw - 1) / (nw * q.tpw);
+            const int waste = nz * nw * q.tpw - q.tiles;
+            if (waste < best_waste) { best_waste = waste; q.nwarps = nw; q.nz = nz; }
+        }
+    }
+    // batch chunks: about a third of the SMs in total, but at least ~3 quads per lane and what fits in smem
+    const int qpi = g.H * g.W / 4;
+    q.XN = g.Cg * g.H * g.W;
+    const size_t per_img = (size_t)2 * q.XN * sizeof(float);
+    int want = (kNumSM / 3 + g.groups * q.nz - 1) / (g.groups * q.nz);
+    if (want < 1) want = 1;
+    int per_chunk = (g.B + want - 1) / want;
+    while (per_chunk * qpi < 96 && per_chunk < g.B) per_chunk++;
+    const int fit = (int)(((size_t)kMaxSmemBytes - 64) / per_img);
+    if (fit < 1) return q;
+    if (per_chunk > fit) per_chunk = fit;
+    q.per_chunk = per_chunk;
+    q.nchunks = (g.B + per_chunk - 1) / per_chunk;
+    q.smem_bytes = 64 + (size_t)per_chunk * per_img;
+    const size_t img_bytes = (size_t)q.XN * sizeof(float);
+    if (img_bytes % 16 != 0) return q;
+    q.ok = true;
+    return q;
+}
+
+struct QuadParams {
+    const float *dx, *y;
+    float *partial;
+    int B, C, H, W, Cg, ntk, tiles, tpw, per_chunk, XN, orient, bulk;
+    int qpi, qpr;              // quads per image / per row
+    unsigned m_qpi, m_qpr;     // ceil(2^32 / qpi), ceil(2^32 / qpr)
+};
+
+template <int KH, int KW, int TC, int TKC, bool FW>
+__global__ void __launch_bounds__(kQuadMaxWarps * 32)
+bwd_weight_quad_kernel(const QuadParams p)
+{
+    constexpr int K = KH * KW, NACC = TC * TKC * K;
+    extern __shared__ __align__(128) float smem[];
+    const int W = p.W, HW = p.H * p.W, Cg = p.Cg;
+    const int chunk = blockIdx.x, G = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    float *buf = smem + 16;                                   // [image][dX planes | y planes]
+    const float *zero4 = smem + 4;                            // 16 zero bytes (see the neighbour loads)
+    if (tid < 4) smem[4 + tid] = 0.f;
+    const int b_begin = chunk * p.per_chunk;
+    const int n_img = (b_begin + p.per_chunk < p.B ? b_begin + p.per_chunk : p.B) - b_begin;
+    const size_t img_stride = (size_t)p.C * HW;
+    const float *dx0 = p.dx + (size_t)G * Cg * HW + (size_t)b_begin * img_stride;
+    const float *y0 = p.y + (size_t)G * Cg * HW + (size_t)b_begin * img_stride;
+    const uint32_t img_bytes = (uint32_t)(Cg * HW) * 4u;
+    const int XN = p.XN;
+
+    if (p.bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, 2u * img_bytes * (uint32_t)n_img);
+            for (int i = 0; i < n_img; i++) {
+                bulk_load(buf + (size_t)(2 * i) * XN, dx0 + (size_t)i * img_stride, img_bytes, bar);
+                bulk_load(buf + (size_t)(2 * i + 1) * XN, y0 + (size_t)i * img_stride, img_bytes, bar);
+            }
+        }
+        __syncthreads();
+        mbar_wait(bar, 0);
+    } else {
+        for (int i = 0; i < n_img; i++)
+            for (int e = tid; e < Cg * HW; e += blockDim.x) {
+                buf[(size_t)(2 * i) * XN + e] = __ldg(dx0 + (size_t)i * img_stride + e);
+                buf[(size_t)(2 * i + 1) * XN + e] = __ldg(y0 + (size_t)i * img_stride + e);
+            }
+        __syncthreads();
+    }
+
+    const bool fh = p.orient & 2;
+    const int rstep = fh ? W : -W;            // row of tap qh: h - qh (or h + qh on a reflected axis)
+    const int nquads = n_img * p.qpi;
+    float *out = p.partial + ((size_t)chunk * p.C + (size_t)G * Cg) * Cg * K;   // [c][kc][t]
+
+    for (int tw = 0; tw < p.tpw; tw++) {
+        const int tile = (blockIdx.z * (blockDim.x >> 5) + warp) * p.tpw + tw;
+        if (tile >= p.tiles) break;                              // warp-uniform
+        const int c0 = (tile / p.ntk) * TC, k0 = (tile % p.ntk) * TKC;
+        float acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; i++) acc[i] = 0.f;
+        for (int u = lane; u < nquads; u += 32) {
+            const int img = p.m_qpi ? (int)__umulhi((unsigned)u, p.m_qpi) : u, r = u - img * p.qpi;     // magic 0: divisor 1
+            const int h = p.m_qpr ? (int)__umulhi((unsigned)r, p.m_qpr) : r, wq = r - h * p.qpr;
+            const float *dimg = buf + (size_t)(2 * img) * XN, *yimg = dimg + XN;
+            const int pix = h * W + 4 * wq;
+            float4 d4[TC];
+#pragma unroll
+            for (int i = 0; i < TC; i++) d4[i] = *reinterpret_cast<const float4 *>(dimg + (c0 + i) * HW + pix);
+            // window of 8 columns per (y channel, tap row): [4wq-4, 4wq+3], reflected: [4wq, 4wq+7]
+            // neighbours outside the image read a zeroed 16-byte cell instead: no branch, no predicated load
+            const bool side_ok = FW ? (wq + 1 < p.qpr) : (wq > 0);
+            const float *ybase = yimg + k0 * HW + pix;
+            const float *row_ptr[KH], *side_ptr[KH];
+#pragma unroll
+            for (int qh = 0; qh < KH; qh++) {
+                const int hh = fh ? h + qh : h - qh;
+                const bool row_ok = hh >= 0 && hh < p.H;
+                row_ptr[qh] = row_ok ? ybase + qh * rstep : zero4;
+                side_ptr[qh] = row_ok && side_ok ? ybase + qh * rstep + (FW ? 4 : -4) : zero4;
+            }
+#pragma unroll
+            for (int k = 0; k < TKC; k++) {
+#pragma unroll
+                for (int qh = 0; qh < KH; qh++) {
+                    // a4: the quad's own columns, b4: the four columns beside it (channel k0 + k: k planes further;
+                    // the zero cell is re-read for every k, its offset masked to 0)
+                    const bool rz = row_ptr[qh] == zero4, sz = side_ptr[qh] == zero4;
+                    const float4 a4 = *reinterpret_cast<const float4 *>(row_ptr[qh] + (rz ? 0 : k * HW));
+                    const float4 b4 = *reinterpret_cast<const float4 *>(side_ptr[qh] + (sz ? 0 : k * HW));
+                    // win[j]: column 4wq - 4 + j (plain) / 4wq + j (reflected)
+                    const float win[8] = {FW ? a4.x : b4.x, FW ? a4.y : b4.y, FW ? a4.z : b4.z, FW ? a4.w : b4.w,
+                                          FW ? b4.x : a4.x, FW ? b4.y : a4.y, FW ? b4.z : a4.z, FW ? b4.w : a4.w};
+                    // pixel j outermost: the TC*KW FMAs of one j are independent of each other, so the
+                    // dependent chain of an accumulator is spaced TC*KW instructions apart
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+#pragma unroll
+                        for (int qw = 0; qw < KW; qw++) {
+#pragma unroll
+                            for (int i = 0; i < TC; i++) {
+                                const float dv = j == 0 ? d4[i].x : (j == 1 ? d4[i].y : (j == 2 ? d4[i].z : d4[i].w));
+                                float &a = acc[((i * TKC + k) * KH + qh) * KW + qw];
+                                a = fmaf(dv, win[FW ? j + qw : 4 + j - qw], a);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        Halve<NACC, 32>::run(acc, lane);
+        int off, size;
+        rs_owner(NACC, 32, lane, &off, &size);
+        constexpr int kFinal = halve_final(NACC, 32);
+#pragma unroll
+        for (int i = 0; i < kFinal; i++) {
+            const int e = off + i;
+            const int t = e % K, ik = (e / K) % TKC, ic = e / (K * TKC);
+            if (i < size) out[((size_t)(c0 + ic) * Cg + (k0 + ik)) * K + t] = acc[i];
+        }
+    }
+}
+
+static int launch_bwd_weight_quad(const Geometry &g, const QuadPlan &q, const float *dx, const float *y, void *workspace,
+                                  cudaStream_t s)
+{
+    QuadParams p{};
+    p.dx = dx; p.y = y; p.partial = (float *)workspace;
+    p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W; p.Cg = g.Cg;
+    p.ntk = g.Cg / kQuadTKC; p.tiles = q.tiles; p.tpw = q.tpw; p.per_chunk = q.per_chunk; p.XN = q.XN;
+    p.orient = g.orient;
+    p.qpr = g.W / 4; p.qpi = g.H * p.qpr;
+    // ceil(2^32 / d): u / d == umulhi(u, m) for the small indices used; d == 1 is flagged by m == 0
+    p.m_qpi = p.qpi > 1 ? (unsigned)((0x100000000ULL + (unsigned)p.qpi - 1) / (unsigned)p.qpi) : 0u;
+    p.m_qpr = p.qpr > 1 ? (unsigned)((0x100000000ULL + (unsigned)p.qpr - 1) / (unsigned)p.qpr) : 0u;
+    p.bulk = (((uintptr_t)dx | (uintptr_t)y) % 16 == 0) && !env().nobulk ? 1 : 0;
+    dim3 grid(q.nchunks, g.groups, q.nz);
+    void (*kern)(const QuadParams) = (g.orient & 1) ? bwd_weight_quad_kernel<3, 3, kQuadTC, kQuadTKC, true>
+                                                    : bwd_weight_quad_kernel<3, 3, kQuadTC, kQuadTKC, false>;
+    if (q.smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<grid, q.nwarps * 32, q.smem_bytes, s>>>(p);
+    return cuda_status(cudaGetLastError());
+}
+
 // one WARP per dW element: lanes stride over the chunks, then a fixed butterfly -- the summation
 // tree depends only on (nchunks), never on timing, so the result stays bit-reproducible
 __global__ void __launch_bounds__(256)
@@ -333,9 +540,24 @@ bwd_weight_reduce_thread_kernel(const float *__restrict__ partial, float *__rest
     }
 }
 
+static bool use_quad(const Geometry &g, QuadPlan *q)
+{
+    *q = make_quad_plan(g);
+    return q->ok && !env().dw_quad_off;
+}
+
+static int stage1_chunks(const Geometry &g)
+{
+    QuadPlan q;
+    if (use_quad(g, &q)) return q.nchunks;
+    return make_plan(g).nchunks;
+}
+
 int launch_bwd_weight_partial(const Geometry &g, const float *dx, const float *y, void *workspace, cudaStream_t s)
 {
     if (g.B == 0) return 0;
+    QuadPlan q;
+    if (use_quad(g, &q)) return launch_bwd_weight_quad(g, q, dx, y, workspace, s);
     const BwdWeightPlan pl = make_plan(g);
     BwdWeightParams p{};
     p.dx = dx; p.y = y; p.partial = (float *)workspace;
@@ -365,9 +587,8 @@ int launch_bwd_weight_reduce(const Geometry &g, int count, const void *workspace
                              float *dw, size_t dw_stride, cudaStream_t s)
 {
     if (count <= 0) return 0;
-    const BwdWeightPlan pl = make_plan(g);
     const int total = g.C * g.Cw * g.K;
-    const int nchunks = g.B > 0 ? pl.nchunks : 0;
+    const int nchunks = g.B > 0 ? stage1_chunks(g) : 0;
     const size_t pstride = workspace_stride / sizeof(float);
     if (nchunks >= 16) {
         int blocks = (total + 7) / 8;             // 8 warps per CTA, one element per warp

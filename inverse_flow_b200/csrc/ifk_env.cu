@@ -11,6 +11,7 @@ namespace ifk {
 static EnvKnobs g_env;
 static std::once_flag g_env_once;
 static std::mutex g_env_mutex;
+static unsigned g_env_generation = 0;
 
 static bool is_one(const char *name)
 {
@@ -32,6 +33,7 @@ static void parse_env()
     k.shfl_off = is_zero("IFK_SOLVE_SHFL");
     k.wave_off = is_zero("IFK_SOLVE_WAVE");
     k.nobulk = is_one("IFK_SOLVE_NOBULK");
+    k.dw_quad_off = is_zero("IFK_DW_QUAD");
     k.pdl = !is_zero("IFK_PDL");
     if (const char *e = getenv("IFK_SHFL_NCT")) k.shfl_nct = atoi(e);
     k.conv_wide = -1;
@@ -46,6 +48,7 @@ static void parse_env()
         sscanf(e, "%d,%d,%d,%d", &k.wave_cfg[0], &k.wave_cfg[1], &k.wave_cfg[2], &k.wave_cfg[3]);
     std::lock_guard<std::mutex> lock(g_env_mutex);
     g_env = k;
+    g_env_generation++;
 }
 
 const EnvKnobs &env()
@@ -68,6 +71,13 @@ static int query_attr(cudaDeviceAttr attr, int fallback)
         return fallback;
     }
     return v;
+}
+
+unsigned env_generation()
+{
+    std::call_once(g_env_once, parse_env);
+    std::lock_guard<std::mutex> lock(g_env_mutex);
+    return g_env_generation;
 }
 
 int device_sm_count()

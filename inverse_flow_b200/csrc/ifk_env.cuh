@@ -12,6 +12,7 @@ struct EnvKnobs {
     bool shfl_off;       // IFK_SOLVE_SHFL=0    : no shuffle kernel
     bool wave_off;       // IFK_SOLVE_WAVE=0    : no pipelined wavefront kernel (-> the older resident kernel)
     bool nobulk;         // IFK_SOLVE_NOBULK=1  : no TMA bulk staging
+    bool dw_quad_off;    // IFK_DW_QUAD=0       : dW stage 1 by the per-tap kernel also where the quad kernel applies
     bool pdl;            // IFK_PDL=0 switches programmatic dependent launch off
     int shfl_nct;        // IFK_SHFL_NCT        : tuning
     int conv_wide;       // IFK_CONV_WIDE       : -1 unset, 0 / 1 forced
@@ -25,6 +26,7 @@ struct EnvKnobs {
 
 const EnvKnobs &env();
 void reload_env();
+unsigned env_generation();    // bumped by reload_env(): memoised kernel selections start over
 
 int device_sm_count();        // cudaDevAttrMultiProcessorCount of the current device (148 on B200; cached)
 int device_max_smem_optin();  // cudaDevAttrMaxSharedMemoryPerBlockOptin (227 KB on B200; cached)

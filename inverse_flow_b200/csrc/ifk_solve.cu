@@ -203,16 +203,14 @@ static SolveConfig choose_config(const Geometry &g)
     typedef std::tuple<int, int, int, int, int, int, int> Key;
     static std::map<Key, SolveConfig> cache;
     static std::mutex mu;
-    static EnvKnobs seen;
-    static bool have_seen = false;
-    const EnvKnobs &k = env();
+    static unsigned seen_generation = 0;
+    const unsigned gen = env_generation();
     const int bcap = 4 * kNumSM;
     const Key key(g.Cg, g.H, g.W, g.KH, g.KW, g.groups, g.B < bcap ? g.B : bcap);
     std::lock_guard<std::mutex> lock(mu);
-    if (!have_seen || memcmp(&seen, &k, sizeof(EnvKnobs)) != 0) {     // knobs reloaded (tests): start over
+    if (seen_generation != gen) {                                     // knobs reloaded (tests): start over
         cache.clear();
-        seen = k;
-        have_seen = true;
+        seen_generation = gen;
     }
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;

@@ -573,15 +573,13 @@ static WaveConfig choose_wave(const Geometry &g)
     typedef std::tuple<int, int, int, int, int, int, int> Key;
     static std::map<Key, WaveConfig> cache;
     static std::mutex mu;
-    static const EnvKnobs *seen = nullptr;
-    static EnvKnobs seen_copy;
-    const EnvKnobs &k = env();
+    static unsigned seen_generation = 0;
+    const unsigned gen = env_generation();
     const Key key(g.C, g.H, g.W, g.KH, g.KW, g.groups, g.B < device_sm_count() ? g.B : device_sm_count());
     std::lock_guard<std::mutex> lock(mu);
-    if (!seen || memcmp(&seen_copy, &k, sizeof(EnvKnobs)) != 0) {     // knobs reloaded (tests): start over
+    if (seen_generation != gen) {                                     // knobs reloaded (tests): start over
         cache.clear();
-        seen_copy = k;
-        seen = &k;
+        seen_generation = gen;
     }
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;

@@ -80,25 +80,53 @@ class InvConvStack:
             self.stages.append(st)
         # dW stage 1 of the layers are independent of each other: several side streams let them overlap
         # (one stream would serialise them and become the critical path once the solves are fast)
-        self.sides = [torch.cuda.Stream(device=self.device) for _ in range(int(os.environ.get("IFK_STACK_SIDE_STREAMS", "8")))]
+        # (lowest priority: the dependent chain of solves on the capturing stream gets freed SMs first)
+        self.sides = [torch.cuda.Stream(device=self.device, priority=0)
+                      for _ in range(int(os.environ.get("IFK_STACK_SIDE_STREAMS", "8")))]
+        self.main = torch.cuda.Stream(device=self.device, priority=-1)      # the stream graphs are captured on
         self._side_rr = 0
         self._sides_forked = []           # side streams forked since the last join (a graph capture must
                                           # only join streams that are part of it)
         self.graph = None
-        # per stage: 1 prepare + n inverse + n dX + n dW stage 1 + 1 dW stage 2
-        self.launches_per_step = sum(3 * st.n + 2 for st in self.stages)
+        # per stage: prepare (+ the wave kernel's weight pack) + n inverse + n dX + n dW stage 1 + 1 dW stage 2
+        self.launches_per_step = sum(3 * st.n + 2 + (1 if "wave<" in _native.describe_solve(st.problem) else 0)
+                                     for st in self.stages)
 
     # -- raw launches ------------------------------------------------------------------
     def _stream(self):
         return _native.current_stream(self.device)
 
-    def forward_stage(self, st):
+    def prepare_stage(self, st, stream=None):
+        """T-fold (and pack) the weights of all the stage's layers: one batched launch pair"""
+        s = self._stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)
+        _native.check(self.lib.ifk_prepare_many_f32(ctypes.byref(st.problem), st.n, st.w_base.data_ptr(), st.w_stride,
+                                                    st.prepared_all.data_ptr(), st.pf, s))
+
+    def prepare_all_forked(self):
+        """the prepares of every stage depend on the weights only: forked onto a side stream at the start of
+        the step, stage k's runs while the earlier stages' solves do; forward_stage joins it"""
+        main = torch.cuda.current_stream(self.device)
+        self._prep_events = {}
+        side = self.sides[-1]
+        side.wait_stream(main)
+        for st in self.stages[1:]:
+            self.prepare_stage(st, side)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            self._prep_events[id(st)] = ev
+        self.prepare_stage(self.stages[0])      # (the waits in forward_stage join the side stream again)
+
+    def forward_stage(self, st, prepared=False):
         lib, s = self.lib, self._stream()
         p = ctypes.byref(st.problem)
-        _native.check(lib.ifk_prepare_many_f32(p, st.n, st.w_base.data_ptr(), st.w_stride,
-                                               st.prepared_all.data_ptr(), st.pf, s))
+        if not prepared:
+            self.prepare_stage(st)
+        elif id(st) in getattr(self, "_prep_events", {}):
+            torch.cuda.current_stream(self.device).wait_event(self._prep_events.pop(id(st)))
         ps = ctypes.byref(st.problem_stable)
         for i in range(st.n):
+            # the first solve follows the prepare (or the join with it): it fetches its weights after the
+            # dependency wait; the others vouch that their predecessor did not write them
             _native.check(lib.ifk_inverse_f32(p if i == 0 else ps, st.act[i].data_ptr(), st.prepared[i].data_ptr(),
                                               st.act[i + 1].data_ptr(), s))
 
@@ -124,8 +152,9 @@ class InvConvStack:
             g = dx
         st.dx = g
 
-    def finish_weight_gradients(self, stages=None):
-        """join the side streams, then one batched dW stage 2 per stage into the flat bucket."""
+    def finish_weight_gradients(self, stages=None, local=False):
+        """join the side streams, then one batched dW stage 2 per stage into the flat bucket (`local`: into the
+        communicator's peer-mapped bucket, see attach_comm)."""
         main = torch.cuda.current_stream(self.device)
         for side in self._sides_forked:
             main.wait_stream(side)
@@ -134,11 +163,12 @@ class InvConvStack:
         for st in (self.stages if stages is None else stages):
             _native.check(self.lib.ifk_bwd_weight_reduce_many_f32(
                 ctypes.byref(st.problem), st.n, st.workspace.data_ptr(), st.ws_floats * 4,
-                st.dw_base.data_ptr(), st.w_stride, s))
+                (st.dw_local_base if local else st.dw_base).data_ptr(), st.w_stride, s))
 
     def forward(self):
+        self.prepare_all_forked()
         for st in self.stages:
-            self.forward_stage(st)
+            self.forward_stage(st, prepared=True)
 
     def backward(self):
         for st in self.stages:
@@ -159,7 +189,7 @@ class InvConvStack:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=self.main):
                 self.forward_backward()
         return self
 
@@ -173,12 +203,12 @@ class InvConvStack:
                 self.capture()                    # warm-up and the single-graph variant
             last, rest = self.stages[-1:], self.stages[:-1]
             self.graph_a, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_a):
+            with torch.cuda.graph(self.graph_a, stream=self.main):
                 self.forward()
                 for st in last:
                     self.backward_stage(st)
                 self.finish_weight_gradients(last)
-            with torch.cuda.graph(self.graph_b):
+            with torch.cuda.graph(self.graph_b, stream=self.main):
                 for st in rest:
                     self.backward_stage(st)
                 self.finish_weight_gradients(rest)
@@ -187,6 +217,67 @@ class InvConvStack:
             self.bucket_last = self.grad_bucket[n_all - n_last:]
             self.bucket_rest = self.grad_bucket[:n_all - n_last]
         return self
+
+    def attach_comm(self, comm):
+        """Data-parallel mode: the stage-2 reductions write this rank's dW into `comm.bucket` (peer-mapped
+        memory, parallel.PeerAllReduce) and the fused peer all-reduce leaves the sum over ranks in
+        `grad_bucket` -- so the exchange needs no copy in between."""
+        if comm.numel != self.grad_bucket.numel():
+            raise ValueError("communicator bucket size differs from the gradient bucket")
+        self.comm = comm
+        off = 0
+        for st in self.stages:
+            st.dw_local_base = comm.bucket[off:]
+            off += st.n * st.w_stride
+        return self
+
+    def capture_parallel(self):
+        """ONE graph per step for data-parallel runs: forward, backward, and the gradient exchange as two
+        launches of the fused peer all-reduce kernel -- the last stage's slice of the bucket (final first, as
+        in a real model) on a side stream while the remaining backward runs, the rest at the end."""
+        comm = self.comm
+        with torch.cuda.device(self.device):
+            if self.graph is None:
+                self.capture()                    # warm-up (sets function attributes) and the local variant
+            last, rest = self.stages[-1:], self.stages[:-1]
+            n_last = sum(st.n * st.w_stride for st in last)
+            n_all = self.grad_bucket.numel()
+            split = n_all - n_last
+            if split % 4:                         # slices start at multiples of 4 floats: otherwise one exchange at the end
+                last, rest, split = self.stages, [], 0
+
+            def run():
+                main = torch.cuda.current_stream(self.device)
+                self.forward()
+                for st in last:
+                    self.backward_stage(st)
+                self.finish_weight_gradients(last, local=True)
+                side = self.sides[-1]
+                if rest:
+                    side.wait_stream(main)                       # fork: the last stage's slice travels now
+                    with torch.cuda.stream(side):
+                        comm.allreduce(self.grad_bucket, offset=split, numel=n_all - split)
+                    for st in rest:
+                        self.backward_stage(st)
+                    self.finish_weight_gradients(rest, local=True)
+                    comm.allreduce(self.grad_bucket, offset=0, numel=split)
+                    main.wait_stream(side)                       # join
+                else:
+                    comm.allreduce(self.grad_bucket)
+
+            warm = torch.cuda.Stream()
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                run()
+            torch.cuda.current_stream().wait_stream(warm)
+            torch.cuda.synchronize()
+            self.graph_parallel = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_parallel, stream=self.main):
+                run()
+        return self
+
+    def step_parallel(self):
+        self.graph_parallel.replay()
 
     def step(self):
         """one forward+backward over the resident batch (device buffers)."""
@@ -256,7 +347,7 @@ class InvConvStack:
             torch.cuda.current_stream().wait_stream(warm)
             torch.cuda.synchronize()
             self.graph_host = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_host):
+            with torch.cuda.graph(self.graph_host, stream=self.main):
                 self._host_pipeline(hb)
         self._host_buffers = hb
         return self

@@ -39,10 +39,15 @@ def test_version_and_status_strings(lib):
 
 def test_sizes(lib):
     p = _native.problem(100, 12, 16, 16, 3, 3, 12, 1)
-    # 2 directions x C rows x round_up(K*Cg, 4)
-    assert lib.ifk_prepared_floats(ctypes.byref(p)) == 2 * 12 * 108
+    # canonical rows: 2 directions x C rows x round_up(K*Cg, 4); geometries the pipelined wavefront kernel serves
+    # carry its lane-major packed copy and entry codes behind them (a multiple of 4 floats: 16-byte strides)
+    n = lib.ifk_prepared_floats(ctypes.byref(p))
+    assert n > 2 * 12 * 108 and n % 4 == 0
     p4 = _native.problem(100, 12, 16, 16, 3, 3, 12, 4)
-    assert lib.ifk_prepared_floats(ctypes.byref(p4)) == 2 * 12 * 28
+    assert lib.ifk_prepared_floats(ctypes.byref(p4)) == 2 * 12 * 28          # Cg = 3: shuffle kernel, no packed copy
+    p2 = _native.problem(100, 4, 14, 14, 2, 2, 4, 1)
+    assert lib.ifk_prepared_floats(ctypes.byref(p2)) == 2 * 4 * 16
+    assert lib.ifk_prepared_floats(ctypes.byref(_native.problem(7, 12, 5, 9, 3, 3, 12, 1))) == n   # size-independent
     ws = lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(p))
     assert ws > 0 and ws % (12 * 12 * 9 * 4) == 0
 

@@ -92,6 +92,8 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--skip-dw", action="store_true")
     ap.add_argument("--dw-child", nargs=4, type=int, default=None)
+    ap.add_argument("--shapes", default=None, help='"B,C,H,k;B,C,H,k;..." instead of the built-in list')
+    ap.add_argument("--ref-only", action="store_true", help="time the reference extension only")
     args = ap.parse_args()
     if args.dw_child:
         ref_dw_child(*args.dw_child, args.iters)
@@ -102,7 +104,8 @@ def main():
         return 0
     gen = torch.Generator().manual_seed(0)
     lines = []
-    for (B, C, H, k) in SHAPES:
+    shapes = SHAPES if not args.shapes else [tuple(int(v) for v in sh.split(",")) for sh in args.shapes.split(";")]
+    for (B, C, H, k) in shapes:
         w = make_weight(C, k, gen).cuda()
         torch.manual_seed(0)
         x = torch.randn(B, C, H, H, device="cuda")
@@ -125,6 +128,10 @@ def main():
             except subprocess.TimeoutExpired:
                 rec["ref_dw_error"] = "timeout"
 
+        if args.ref_only:
+            print(json.dumps(rec), flush=True)
+            lines.append(rec)
+            continue
         prep = IF.prepare(w, groups=4)
         y = IF.inverse(x, w, groups=4, prepared=prep)
         dx = IF.bwd_input(g, w, groups=4, prepared=prep)
