@@ -564,203 +564,6 @@ def run_ours(args):
 
     line = base_line(args, stages, batch, desc, n_gpus)
     line.update({
-        "impl": "reference", "value": value, "ms_per_step": per * 1e3, "steps": len(times),
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "full step (batch %d, all layers), float32 oracle port with OpenMP; the "
-                                   "reference has no CPU backward" % batch,
-                         "reference_cython_inverse_only_images_per_s":
-                             ref_cython_inverse_rate(weights, xs) if all(g == 1 for g in groups_of) else None,
-                         "reference_cython_openmp_inverse_only_images_per_s":
-                             ref_cython_inverse_rate(weights, xs, module="solve_parallel_mc_omp")
-                             if all(g == 1 for g in groups_of) else None},
-        "gpu_launches": 0,
-    })
-    line["config"]["parallelism"] = "host cores of rank 0 only (%d OpenMP threads)" % threads
-    print(json.dumps(line))
-    return 0
-
-
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from inverse_flow_b200 import _native
-    from inverse_flow_b200.stack import InvConvStack
-    from oracle import oracle
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        # NCCL carries the rendezvous and the timing reductions only; its log (NCCL_DEBUG, if the launcher set it)
-        # goes to stderr so that stdout stays ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=device)
-    n_gpus = world
-
-    stages, batch, desc = WORKLOADS[args.workload]
-    stack = InvConvStack(stages, batch, groups=args.groups, device=device, seed=0)
-    weights, _, _, groups_of = host_data(stages, 1, args.groups, seed=0)      # same on every rank
-    _, xs, gs, _ = host_data(stages, batch, args.groups, seed=1000 + rank)    # this rank's shard
-    for st, ws in zip(stack.stages, weights):
-        for wt, w in zip(st.w, ws):
-            wt.copy_(torch.from_numpy(w))
-    for st, x, g in zip(stack.stages, xs, gs):
-        st.act[0].copy_(torch.from_numpy(x))
-        st.grad_in.copy_(torch.from_numpy(g))
-    stack.capture()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
-
-    comm_kind = None
-    if world > 1:
-        # the gradient exchange: the fused peer-memory all-reduce kernel inside the step's ONE graph
-        # (inverse_flow_b200/parallel.py, csrc/ifk_comm.cu); --comm nccl keeps NCCL (two graphs + host-issued
-        # all-reduces, the round-1 scheme) for comparison
-        if args.comm == "peer":
-            from inverse_flow_b200.parallel import PeerAllReduce
-            stack.attach_comm(PeerAllReduce(stack.grad_bucket.numel(), device))
-            stack.capture_parallel()
-            comm_kind = "peer: ifk_allreduce_peer_f32 (one-shot over NVLink peer mappings, rank-ordered sum), in the step graph"
-        else:
-            stack.capture_bucketed()
-            comm_kind = "nccl: two dist.all_reduce per step between two graph replays"
-
-    def one_step():
-        if world == 1:
-            stack.step()
-        elif args.comm == "peer":
-            stack.step_parallel()
-        else:
-            stack.graph_a.replay()
-            h = dist.all_reduce(stack.bucket_last, async_op=True)
-            stack.graph_b.replay()
-            if stack.bucket_rest.numel():
-                dist.all_reduce(stack.bucket_rest)
-            h.wait()
-
-    def timed(fn, steps):
-        tot = 0.0
-        for _ in range(steps):
-            flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            fn()
-            e.record()
-            e.synchronize()
-            tot += s.elapsed_time(e)
-        return tot            # ms
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident throughput -------------------------------------------------------
-    with ClockSampler(local) as clk:              # sampling spans warm-up + timed region (nvidia-smi is slow to start)
-        t_up = time.perf_counter()
-        for _ in range(max(args.warmup, 3)):
-            flush.zero_()
-            one_step()
-        while rank == 0 and not clk.rows and time.perf_counter() - t_up < 3.0:
-            flush.zero_()
-            stack.step()                          # local work only (no collective): load until the first sample
-        barrier()
-        total_ms = timed(one_step, args.steps)
-        barrier()
-    total_ms = max_over_ranks(total_ms)
-    ms_per_step = total_ms / args.steps
-    value = batch * n_gpus / (ms_per_step * 1e-3)
-
-    # ---- end to end from pinned host buffers ----------------------------------------------
-    hb = stack.make_host_buffers()
-    for x_h, g_h, x, g in zip(hb["x"], hb["g"], xs, gs):
-        x_h.copy_(torch.from_numpy(x))
-        g_h.copy_(torch.from_numpy(g))
-    bytes_io = [0, 0]
-
-    def one_step_host():
-        if world > 1:
-            h2d = d2h = 0
-            for st, x, g in zip(stack.stages, hb["x"], hb["g"]):
-                st.act[0].copy_(x, non_blocking=True)
-                st.grad_in.copy_(g, non_blocking=True)
-                h2d += 2 * x.numel() * 4
-            one_step()
-            for st, y, dx in zip(stack.stages, hb["y"], hb["dx"]):
-                y.copy_(st.act[st.n], non_blocking=True)
-                dx.copy_(st.dx, non_blocking=True)
-                d2h += 2 * y.numel() * 4
-            hb["dw"].copy_(stack.grad_bucket, non_blocking=True)
-            d2h += hb["dw"].numel() * 4
-            torch.cuda.current_stream().synchronize()
-            bytes_io[0], bytes_io[1] = h2d, d2h
-        else:
-            bytes_io[0], bytes_io[1] = stack.step_host(hb)
-
-    for _ in range(max(args.warmup, 3)):
-        one_step_host()
-    barrier()
-    e2e_ms = max_over_ranks(timed(one_step_host, args.steps)) / args.steps
-    barrier()
-    e2e_value = batch * n_gpus / (e2e_ms * 1e-3)
-
-    # ---- dominant kernel: the wavefront solve at the first stage's shape --------------------
-    st0 = stack.stages[0]
-    import ctypes
-    lib = stack.lib
-    reps = 64
-    solve_graph = torch.cuda.CUDAGraph()
-    p0 = ctypes.byref(st0.problem)
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        _native.check(lib.ifk_inverse_f32(p0, st0.act[0].data_ptr(), st0.prepared[0].data_ptr(),
-                                          st0.act[1].data_ptr(), _native.current_stream(device)))
-    torch.cuda.synchronize()
-    with torch.cuda.graph(solve_graph):
-        for i in range(reps):
-            _native.check(lib.ifk_inverse_f32(p0, st0.act[0].data_ptr(), st0.prepared[0].data_ptr(),
-                                              st0.act[1].data_ptr(), _native.current_stream(device)))
-    solve_ms = timed(solve_graph.replay, 5) / 5 / reps
-    N0 = batch * st0.C * st0.H * st0.W
-    Cg0 = st0.C // st0.groups
-    solve_bytes = 4 * (2 * N0 + st0.C * Cg0 * st0.k * st0.k)
-    peak, peak_src = measured_peak_gbs()
-    achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
-    n_solves = sum(2 * s.n for s in stack.stages)
-    roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": PROFILED_DRAM_TRAFFIC.get(args.workload, (None, None))[0] if args.groups == 1 else None,
-        "traffic_source": PROFILED_DRAM_TRAFFIC.get(args.workload, (None, None))[1] if args.groups == 1 else None,
-        "peak_source": peak_src,
-        "kernel": "%s (wavefront triangular solve; inverse and bwd_input)" % solve_kernel_name(
-            _native.describe_solve(st0.problem)),
-        "variant": _native.describe_solve(st0.problem),
-        "kernel_us": solve_ms * 1e3, "algorithmic_bytes_per_launch": solve_bytes,
-        "how": "%d back-to-back launches of ifk_inverse_f32 at stage 1 in a CUDA graph, CUDA events, L2 "
-               "flushed before each replay" % reps,
-        "wavefront_steps_per_launch": st0.H + st0.W - 1,
-        "wavefront_ns_per_diagonal": solve_ms * 1e6 / (st0.H + st0.W - 1),
-        "solve_launches_per_step": n_solves,
-        "note": "latency-bound at model shapes: the image (%.0f KB) moves in well under a microsecond; the "
-                "binding term is the (H+W-1)-step dependency chain (see DESIGN.md roofline)" % (solve_bytes / 1e3),
-    }
-
-    roofline["wavefront"] = wavefront_step_accounting(lib, p0, st0, device)
-
-    line = base_line(args, stages, batch, desc, n_gpus)
-    line.update({
         "value": value, "ms_per_step": ms_per_step,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": bytes_io[0] * n_gpus,
                 "d2h_bytes_per_step": bytes_io[1] * n_gpus, "ms_per_step": e2e_ms},
@@ -829,6 +632,12 @@ def run_ours(args):
         line["comm"] = {"kind": comm_kind, "bucket_floats": stack.grad_bucket.numel(),
                         "bit_identical_across_ranks": bool(torch.equal(lo, hi)),
                         "finite": bool(torch.isfinite(stack.grad_bucket).all())}
+        if args.comm == "peer":
+            # ... and they must be the sum: NCCL's all-reduce of the same per-rank buckets as the checker
+            ref = stack.comm.bucket.clone()
+            dist.all_reduce(ref)
+            den = float(ref.abs().max()) or 1.0
+            line["comm"]["max_rel_err_vs_nccl_allreduce"] = float((stack.grad_bucket - ref).abs().max()) / den
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -243,7 +243,9 @@ class InvConvStack:
             n_last = sum(st.n * st.w_stride for st in last)
             n_all = self.grad_bucket.numel()
             split = n_all - n_last
-            if split % 4:                         # slices start at multiples of 4 floats: otherwise one exchange at the end
+            # one exchange at the end when the slices would not start at multiples of 4 floats, or when the bucket
+            # is so small that a second hand-shake with the peers costs more than overlapping it could hide
+            if split % 4 or n_all * 4 < 256 * 1024:
                 last, rest, split = self.stages, [], 0
 
             def run():

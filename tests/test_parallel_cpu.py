@@ -51,13 +51,22 @@ def _worker(rank, world, port, B, q):
         y = oracle.inverse(x[lo:hi], w, groups)
         dx, dw = oracle.backward(g[lo:hi], y, w, groups)
         bucket = torch.from_numpy(dw.reshape(-1).copy())
+        # what the fused peer all-reduce kernel computes on the GPUs (csrc/ifk_comm.cu): every rank gathers all
+        # buckets and adds them in rank order -> bit-identical on every rank, equal to the collective sum
+        gathered = [torch.empty_like(bucket) for _ in range(world)]
+        dist.all_gather(gathered, bucket)
+        ordered = parallel.rank_order_sum(gathered)
         parallel.allreduce_gradients(bucket)
+        ranks_agree = [torch.empty_like(ordered) for _ in range(world)]
+        dist.all_gather(ranks_agree, ordered)
+        same_everywhere = all(torch.equal(ranks_agree[0], r) for r in ranks_agree)
+        close_to_collective = torch.allclose(ordered, bucket, rtol=1e-12, atol=1e-12)
         t = parallel.max_over_ranks(float(rank + 1))
         y_full = oracle.inverse(x, w, groups)
         dx_full, dw_full = oracle.backward(g, y_full, w, groups)
         ok = (np.array_equal(y, y_full[lo:hi]) and np.array_equal(dx, dx_full[lo:hi])
               and np.allclose(bucket.numpy(), dw_full.reshape(-1), rtol=1e-12, atol=1e-12)
-              and t == float(world))
+              and t == float(world) and same_everywhere and close_to_collective)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
