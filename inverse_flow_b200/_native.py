@@ -25,6 +25,8 @@ EXPORTS = (
 )
 
 FLAG_STABLE_PREPARED = 1        # enum ifk_flags
+ERR_BAD_LAYOUT = -7              # enum ifk_status
+ERR_UNSUPPORTED = -4
 
 
 class Problem(ctypes.Structure):

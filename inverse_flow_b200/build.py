@@ -22,6 +22,12 @@ NVCC_FLAGS = [
 ]
 
 
+def _host_compiler():
+    """nvcc's host compiler: $CXX, else the first g++ on PATH"""
+    import shutil
+    return os.environ.get("CXX") or shutil.which("g++") or "g++"
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.sep not in cand or os.path.exists(cand)):
@@ -47,7 +53,7 @@ def build_native(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), "-ccbin", "/usr/bin/g++", *flags, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+        cmd = [_nvcc(), "-ccbin", _host_compiler(), *flags, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                                  text=True)))
@@ -63,7 +69,7 @@ def build_native(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [_nvcc(), "-ccbin", "/usr/bin/g++", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [_nvcc(), "-ccbin", _host_compiler(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
            "-o", LIB_PATH, *objs]
     subprocess.check_call(cmd)
     return LIB_PATH

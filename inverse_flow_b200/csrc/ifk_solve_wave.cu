@@ -31,14 +31,17 @@
 
 namespace ifk {
 
+constexpr int kWaveChainMax = 8;      // consecutive layers one launch can take (ifk_inverse_chain_f32)
+
 struct WaveParams {
     const float *in;
-    float *out;
-    const float4 *pack;  // this direction's packed weights (wave_pack_kernel): [group][j][lane of the pixel]
-    const int *codes;    // [group-independent][slot][lane of the pixel]: tap / channel-vector code per entry
+    float *out[kWaveChainMax];          // layer i's output (every layer's y reaches memory: the backward needs it)
+    const float4 *pack[kWaveChainMax];  // layer i's packed weights of this direction (wave_pack_kernel): [group][j][lane]
+    int flips[kWaveChainMax];           // layer i's frame (as SolveParams::flip)
+    int nlayers;                        // 1 for a plain solve
+    const int *codes;    // [slot][lane of the pixel]: tap / channel-vector code per entry (the same for every layer)
     int B, C, H, W;
     int nslots;         // image rows in flight (threads / lanes per pixel)
-    int flip;           // as SolveParams::flip
     int bulk;           // TMA bulk copy of the input image possible (size / alignment)
     int early;          // prepared weights may be fetched ahead of griddepcontrol.wait (ifk.h: IFK_FLAG_*)
     int PS, RSP;        // pixel stride / row stride of the NHWC buffers, floats
@@ -127,7 +130,6 @@ solve_wave_kernel(const WaveParams p)
     const uint32_t img_bytes = (uint32_t)(CG * HW) * 4u;
     const size_t img_stride = (size_t)p.C * HW;
     const float *in0 = p.in + (size_t)G * CG * HW;
-    float *out0 = p.out + (size_t)G * CG * HW;
 
     const int l = tid % LPP, slot = tid / LPP;
     const int ks = l % NS, ct = l / NS;
@@ -138,14 +140,16 @@ solve_wave_kernel(const WaveParams p)
     f32x2_t wreg[2 * NW4];
     int offs[NVF + NVO];
     const int xoff = p.YN * 4;                                  // xh lies YN floats behind yb
-    auto load_weights = [&]() {
-        const ulonglong2 *pk = reinterpret_cast<const ulonglong2 *>(p.pack) + (size_t)G * NW4 * LPP + l;
+    auto load_weights = [&](int li) {
+        const ulonglong2 *pk = reinterpret_cast<const ulonglong2 *>(p.pack[li]) + (size_t)G * NW4 * LPP + l;
 #pragma unroll
         for (int j = 0; j < NW4; j++) {
             const ulonglong2 w4 = __ldg(pk + j * LPP);      // two packed pairs; nothing waits for them here
             wreg[2 * j] = w4.x;
             wreg[2 * j + 1] = w4.y;
         }
+    };
+    auto load_offsets = [&]() {
 #pragma unroll
         for (int j = 0; j < NVF + NVO; j++) {
             const int code = __ldg(p.codes + j * LPP + l);
@@ -160,7 +164,7 @@ solve_wave_kernel(const WaveParams p)
     // before my predecessor has completed and is visible" holds transitively for them.  Either way the
     // weight fetch (one L2 round trip) is in flight while the image lands and is transposed: nothing
     // below needs the weights before the wavefront starts.
-    if (p.early) load_weights();
+    if (p.early) { load_weights(0); load_offsets(); }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int b = blockIdx.x;
@@ -172,7 +176,7 @@ solve_wave_kernel(const WaveParams p)
         }
         smem[2] = 0.f;          // source of the opaque zero used by Hold
     }
-    if (!p.early) load_weights();
+    if (!p.early) { load_weights(0); load_offsets(); }
     // zero halo (and the extra column the look-ahead touches): once per CTA -- the interior of xh is
     // rewritten for every image, the interior of yb is written before it is read
     for (int i = tid * 4; i < 2 * p.YN; i += nthr * 4)
@@ -195,8 +199,7 @@ solve_wave_kernel(const WaveParams p)
     const int Wr = hold(W), nsl = hold(p.nslots);
     own_size = hold(own_size);
     const int slot_r = hold(slot);
-    // memory index of solver pixel (h, w) = idx0 + sh*h*W + sw*w (reflected axes walk backwards)
-    const int sw = (p.flip & 1) ? -1 : 1, sh = (p.flip & 2) ? -1 : 1;
+    // memory index of solver pixel (h, w) of a layer's frame = idx0 + sh*h*W + sw*w (reflected axes walk backwards)
     // the transposing passes: TM pixel lanes x TC channel lanes
     const int TM = 1 << p.tm_shift, TC = nthr >> p.tm_shift;
     const int tm = tid & (TM - 1), tc = tid >> p.tm_shift;
@@ -221,7 +224,7 @@ solve_wave_kernel(const WaveParams p)
         // so are the vector stores.  Loads of up to four vectors are issued before the first store.
         for (int m = tm; m < HW; m += TM) {
             const int hm = (int)__umulhi((unsigned)m, p.mW), wm = m - hm * W;
-            const int h = sh > 0 ? hm : H - 1 - hm, w = sw > 0 ? wm : W - 1 - wm;
+            const int h = (p.flips[0] & 2) ? H - 1 - hm : hm, w = (p.flips[0] & 1) ? W - 1 - wm : wm;
             float *d = xh + ((h + KH - 1) * RSP + (w + KW - 1) * PS) + tc * VEC;
             const float *sp = xbuf + m + tc * VEC * HW;
             const int dstep = TC * VEC, sstep = TC * VEC * HW;
@@ -238,6 +241,7 @@ solve_wave_kernel(const WaveParams p)
         }
         IFK_WPROBE(5);
 
+      for (int li = 0; li < p.nlayers; li++) {      // consecutive layers: the image stays in shared memory
         // ---- wavefront ------------------------------------------------------------------------
         f32x2_t acc[ITERS][CC];          // old part of the row's pixel on the coming diagonal
         // old part (taps two or more diagonals back + T x) of the pixel at `pn`
@@ -311,25 +315,35 @@ solve_wave_kernel(const WaveParams p)
         __syncthreads();
 
         // ---- y leaves: NHWC shared memory -> NCHW global, coalesced (consecutive threads = consecutive
-        //      memory pixels of one channel vector; PS/VEC odd keeps the vector loads conflict free)
-        float *dst = out0 + (size_t)b * img_stride;
+        //      memory pixels of one channel vector; PS/VEC odd keeps the vector loads conflict free).  In a chain the
+        //      same pass hands y to the next layer: into xh, re-indexed from this layer's frame to the next one's.
+        const bool more = li + 1 < p.nlayers;
+        if (more || (p.nlayers > 1 && b_next < p.B)) load_weights(more ? li + 1 : 0);      // in flight during the write-out
+        float *dst = p.out[li] + (size_t)G * CG * HW + (size_t)b * img_stride;
+        const int fl = p.flips[li], fn = more ? p.flips[li + 1] : fl;
         for (int m = tm; m < HW; m += TM) {
             const int hm = (int)__umulhi((unsigned)m, p.mW), wm = m - hm * W;
-            const int h = sh > 0 ? hm : H - 1 - hm, w = sw > 0 ? wm : W - 1 - wm;
+            const int h = (fl & 2) ? H - 1 - hm : hm, w = (fl & 1) ? W - 1 - wm : wm;
+            const int h2 = (fn & 2) ? H - 1 - hm : hm, w2 = (fn & 1) ? W - 1 - wm : wm;
             const float *sp = yb + ((h + KH - 1) * RSP + (w + KW - 1) * PS) + tc * VEC;
+            float *xn = xh + ((h2 + KH - 1) * RSP + (w2 + KW - 1) * PS) + tc * VEC;
             float *d = dst + m + tc * VEC * HW;
             const int sstep = TC * VEC, dstep = TC * VEC * HW;
 #pragma unroll 2
-            for (int cv = tc; cv < CGV; cv += TC, sp += sstep, d += dstep) {
+            for (int cv = tc; cv < CGV; cv += TC, sp += sstep, xn += sstep, d += dstep) {
                 if (VEC == 4) {
                     const float4 t4 = *reinterpret_cast<const float4 *>(sp);
                     d[0] = t4.x; d[HW] = t4.y; d[2 * HW] = t4.z; d[3 * HW] = t4.w;
+                    if (more) *reinterpret_cast<float4 *>(xn) = t4;
                 } else {
                     const float2 t2 = *reinterpret_cast<const float2 *>(sp);
                     d[0] = t2.x; d[HW] = t2.y;
+                    if (more) *reinterpret_cast<float2 *>(xn) = t2;
                 }
             }
         }
+        if (more) __syncthreads();                 // xh holds the next layer's input; yb may be overwritten
+      }
         IFK_WPROBE(7);
         if (b_next < p.B) __syncthreads();          // yb is rewritten by the next image's wavefront
     }
@@ -647,20 +661,29 @@ int launch_wave_pack(const Geometry &g, float *prepared, int count, size_t prepa
     return cuda_status(cudaGetLastError());
 }
 
-int launch_solve_wave(const Geometry &g, const float *in, const float *prepared, float *out, bool reverse,
-                      int flags, long long *probe, cudaStream_t s)
+// one launch over `n` consecutive layers (n == 1: a plain solve).  prepared[i]: layer i's whole prepared buffer.
+static int launch_wave_layers(const Geometry &g, int n, const int *orients, const float *const *prepared, const float *in,
+                              float *const *outs, bool reverse, int flags, long long *probe, cudaStream_t s)
 {
     const WaveConfig c = choose_wave(g);
-    if (!c.ok) return IFK_ERR_UNSUPPORTED;
+    if (!c.ok || n < 1 || n > kWaveChainMax) return IFK_ERR_UNSUPPORTED;
     const WavePackDims d = wave_pack_dims(c.v, g.groups);
-    const float *pack = prepared + (size_t)2 * g.C * g.KDP;
     WaveParams p{};
-    p.in = in; p.out = out;
-    p.pack = reinterpret_cast<const float4 *>(pack + (reverse ? d.pack_floats / 2 : 0));
-    p.codes = reinterpret_cast<const int *>(pack + d.pack_floats);
+    p.in = in;
+    p.nlayers = n;
+    bool aligned = true;
+    for (int i = 0; i < n; i++) {
+        const float *pack = prepared[i] + (size_t)2 * g.C * g.KDP;
+        p.pack[i] = reinterpret_cast<const float4 *>(pack + (reverse ? d.pack_floats / 2 : 0));
+        p.out[i] = outs[i];
+        const int orient = orients ? orients[i] : g.orient;
+        p.flips[i] = reverse ? (orient ^ 3) : orient;      // the adjoint walks the fully reflected frame
+        aligned = aligned && ((uintptr_t)prepared[i] % 16 == 0);
+    }
+    if (!aligned) return IFK_ERR_UNSUPPORTED;               // the packed weights are read as 16-byte words
+    p.codes = reinterpret_cast<const int *>(prepared[0] + (size_t)2 * g.C * g.KDP + d.pack_floats);
     p.B = g.B; p.C = g.C; p.H = g.H; p.W = g.W;
     p.nslots = c.nslots;
-    p.flip = reverse ? (g.orient ^ 3) : g.orient;
     const size_t img_bytes = (size_t)g.Cg * g.H * g.W * sizeof(float);
     p.bulk = (img_bytes % 16 == 0) && ((uintptr_t)in % 16 == 0) && !env().nobulk ? 1 : 0;
     p.early = (flags & IFK_FLAG_STABLE_PREPARED) ? 1 : 0;
@@ -707,10 +730,27 @@ int launch_solve_wave(const Geometry &g, const float *in, const float *prepared,
     return IFK_ERR_UNSUPPORTED;
 }
 
+int launch_solve_wave(const Geometry &g, const float *in, const float *prepared, float *out, bool reverse,
+                      int flags, long long *probe, cudaStream_t s)
+{
+    return launch_wave_layers(g, 1, nullptr, &prepared, in, &out, reverse, flags, probe, s);
+}
+
+// consecutive layers feeding each other (ifk_inverse_chain_f32): groups of up to kWaveChainMax layers per launch
 int launch_solve_chain(const Geometry &g, int n, const int *orients, const float *const *prepared, const float *x,
                        float *const *ys, cudaStream_t s)
 {
-    return IFK_ERR_UNSUPPORTED;
+    if (g.B == 0) return 0;
+    if (!choose_wave(g).ok) return IFK_ERR_UNSUPPORTED;
+    const float *in = x;
+    for (int i = 0; i < n; i += kWaveChainMax) {
+        const int m = n - i < kWaveChainMax ? n - i : kWaveChainMax;
+        // (no IFK_FLAG_STABLE_PREPARED: the caller may have prepared the weights right before)
+        const int st = launch_wave_layers(g, m, orients + i, prepared + i, in, ys + i, false, 0, nullptr, s);
+        if (st != 0) return st;
+        in = ys[i + m - 1];
+    }
+    return 0;
 }
 
 }  // namespace ifk

@@ -28,7 +28,23 @@ def _check_activation(t, name):
     if t.dim() != 4:
         raise ValueError("%s must be 4-D (B, C, H, W), got shape %s" % (name, tuple(t.shape)))
     if not t.is_contiguous():              # reference: CHECK_CONTIGUOUS -> RuntimeError (.cpp:16)
+        if t.is_contiguous(memory_format=torch.channels_last):
+            # IFK_ERR_BAD_LAYOUT (ifk.h): the kernels read NCHW; a channels_last tensor handed over as a raw
+            # pointer would be read as garbage, so it is refused here instead
+            raise RuntimeError("%s is channels_last (NHWC); the inverse-conv kernels take NCHW-contiguous tensors: "
+                               "call .contiguous() first (ifk status %d)" % (name, _native.ERR_BAD_LAYOUT))
         raise RuntimeError("%s must be contiguous" % name)
+
+
+def _check_out(out, like, name):
+    """a caller-allocated output (the reference's call style, inv_conv_with_bp_general.cpp:19-28): same shape,
+    dtype, device as `like`, contiguous, not aliasing it"""
+    _check_activation(out, name)
+    if out.shape != like.shape or out.device != like.device:
+        raise ValueError("%s must match the shape and device of its input: %s on %s vs %s on %s" % (
+            name, tuple(out.shape), out.device, tuple(like.shape), like.device))
+    if out.data_ptr() == like.data_ptr() and like.numel():
+        raise ValueError("%s must not alias its input" % name)
 
 
 def _problem(x, weight, groups, orient=0):
@@ -70,6 +86,12 @@ class Prepared:
             _native.check(lib.ifk_prepare_f32(ctypes.byref(p), _ptr(weight), _ptr(self.buffer),
                                               _native.current_stream(weight.device)))
 
+    def check_weight(self, weight):
+        """the prepared buffer belongs to ONE weight tensor's shape"""
+        if weight is not None and tuple(weight.shape) != self.weight_shape:
+            raise ValueError("prepared weights are for a kernel of shape %s, got %s" % (
+                self.weight_shape, tuple(weight.shape)))
+
     def for_batch(self, x, orient=0):
         C, Cw, KH, KW = self.weight_shape
         if x.shape[1] != C:
@@ -92,20 +114,57 @@ def inverse(x, weight, groups=None, out=None, prepared=None, orient=0):
     lib = _native.load()
     if prepared is None:
         prepared = Prepared(weight, groups)
+    else:
+        prepared.check_weight(weight)
     _check_activation(x, "input")
     p = prepared.for_batch(x, orient)
     if out is None:
         out = torch.empty_like(x)
     else:
-        _check_activation(out, "output")
-        if out.shape != x.shape or out.device != x.device:
-            raise ValueError("output must match input shape/device")
-        if out.data_ptr() == x.data_ptr() and x.numel():
-            raise ValueError("input and output must not alias")
+        _check_out(out, x, "output")
     with torch.cuda.device(x.device):
         _native.check(lib.ifk_inverse_f32(ctypes.byref(p), _ptr(x), _ptr(prepared.buffer), _ptr(out),
                                           _native.current_stream(x.device)))
     return out
+
+
+def inverse_chain(x, prepared_list, orients, outs=None):
+    """Consecutive inverse-conv layers that feed each other -- y_0 = L_0^-1 x, y_i = L_i^-1 y_{i-1} -- as ONE launch
+    (ifk_inverse_chain_f32): the image stays in shared memory from layer to layer; every y_i is still written
+    (the backward needs it).  `prepared_list`: one Prepared per layer (same kernel shape and groups), `orients`:
+    the layers' orders.  Returns the list of outputs, bit-identical to calling `inverse` per layer.  Geometries
+    without a resident chain kernel are served by that per-layer loop."""
+    lib = _native.load()
+    n = len(prepared_list)
+    if n == 0 or len(orients) != n:
+        raise ValueError("need one orientation per layer")
+    _check_activation(x, "input")
+    first = prepared_list[0]
+    if any(pr.weight_shape != first.weight_shape or pr.groups != first.groups for pr in prepared_list):
+        raise ValueError("the layers of a chain share one kernel shape and grouping")
+    if outs is None:
+        outs = [torch.empty_like(x) for _ in range(n)]
+    else:
+        if len(outs) != n:
+            raise ValueError("need one output per layer")
+        for o in outs:
+            _check_out(o, x, "output")
+    p = first.for_batch(x, 0)
+    codes = (ctypes.c_int * n)(*[_native.orient_code(o) for o in orients])
+    preps = (ctypes.c_void_p * n)(*[pr.buffer.data_ptr() for pr in prepared_list])
+    ys = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(x.device):
+        status = lib.ifk_inverse_chain_f32(ctypes.byref(p), n, codes, preps, _ptr(x), ys, _native.current_stream(x.device))
+        if status == _native.ERR_UNSUPPORTED:              # no resident kernel for this geometry: layer by layer
+            cur = x
+            for pr, o, out in zip(prepared_list, orients, outs):
+                q = pr.for_batch(cur, o)
+                _native.check(lib.ifk_inverse_f32(ctypes.byref(q), _ptr(cur), _ptr(pr.buffer), _ptr(out),
+                                                  _native.current_stream(x.device)))
+                cur = out
+        else:
+            _native.check(status)
+    return outs
 
 
 def conv(y, weight, groups=None, out=None, orient=0):
@@ -115,11 +174,7 @@ def conv(y, weight, groups=None, out=None, orient=0):
     if out is None:
         out = torch.empty_like(y)
     else:
-        _check_activation(out, "output")
-        if out.shape != y.shape or out.device != y.device:
-            raise ValueError("output must match input shape/device")
-        if out.data_ptr() == y.data_ptr() and y.numel():
-            raise ValueError("input and output must not alias")
+        _check_out(out, y, "output")
     with torch.cuda.device(y.device):
         _native.check(lib.ifk_conv_f32(ctypes.byref(p), _ptr(y), _ptr(weight), _ptr(out),
                                        _native.current_stream(y.device)))
@@ -131,10 +186,14 @@ def bwd_input(grad, weight, groups=None, out=None, prepared=None, orient=0):
     lib = _native.load()
     if prepared is None:
         prepared = Prepared(weight, groups)
+    else:
+        prepared.check_weight(weight)
     _check_activation(grad, "grad_output")
     p = prepared.for_batch(grad, orient)
     if out is None:
         out = torch.empty_like(grad)
+    else:
+        _check_out(out, grad, "output")
     with torch.cuda.device(grad.device):
         _native.check(lib.ifk_bwd_input_f32(ctypes.byref(p), _ptr(grad), _ptr(prepared.buffer), _ptr(out),
                                             _native.current_stream(grad.device)))
@@ -146,10 +205,15 @@ def bwd_weight(dx, y, weight, groups=None, out=None, orient=0):
     lib = _native.load()
     p = _problem(dx, weight, groups, orient)
     _check_activation(y, "saved output")
-    if y.shape != dx.shape:
-        raise ValueError("dx and y shapes differ")
+    if y.shape != dx.shape or y.device != dx.device:
+        raise ValueError("dx and y shapes / devices differ")
     if out is None:
         out = torch.empty_like(weight)
+    else:
+        _check_activation(out, "output")
+        if out.shape != weight.shape or out.device != weight.device:
+            raise ValueError("the weight gradient must have the kernel's shape %s on %s, got %s on %s" % (
+                tuple(weight.shape), weight.device, tuple(out.shape), out.device))
     nbytes = lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(p))
     ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dx.device)
     with torch.cuda.device(dx.device):
@@ -163,6 +227,8 @@ def backward(grad, y, weight, groups=None, prepared=None, orient=0):
     lib = _native.load()
     if prepared is None:
         prepared = Prepared(weight, groups)
+    else:
+        prepared.check_weight(weight)
     _check_activation(grad, "grad_output")
     _check_activation(y, "saved output")
     if y.shape != grad.shape:

@@ -1,17 +1,21 @@
 """Drop-in for the reference's `inv_conv_with_bp` extension module.
 
-Same four names and argument order as the pybind module exported at
-inf/utils/inv_conv_cuda/inv_conv_with_bp_general.cpp:115-120, so the reference's layer file
-(inf/layers/inv_conv.py:21,52,74,79,266,459) runs unchanged with
+Same four names as the pybind module exported at
+inf/utils/inv_conv_cuda/inv_conv_with_bp_general.cpp:115-120:
 
     import inverse_flow_b200.inv_conv_with_bp as inv_conv_with_bp
 
-Like the reference, each function writes into the caller-allocated `output` and returns
-`[output]`; the scratch tensors `M` the reference needs are accepted and ignored.
-Differences by design: `dy` returns the true input gradient L^-T g and
-`dw` the true weight gradient (the reference's `dw` is fed the layer INPUT; here the third
-positional tensor must be the saved OUTPUT y of `inverse`, see `inv_conv_` in layers/);
-work is enqueued on the current stream without device synchronisation.
+`inverse`, `forward` and `dy` take the reference's positional arguments unchanged; each function writes
+into the caller-allocated `output` and returns `[output]`, and the scratch tensors `M` the reference
+needs are accepted and ignored.  Work is enqueued on the current stream without device synchronisation.
+
+NOT a drop-in for the reference's `inv_conv_.backward` as written (inf/layers/inv_conv.py:62-81): that code
+calls `dw(input_x, kernel, output_grad, M, out)`, i.e. it feeds the layer INPUT and the UPSTREAM gradient,
+which is not what the weight gradient is a function of.  The true gradient is
+dW = -corr(dX, y) with y the saved OUTPUT of `inverse` and dX the result of `dy`, so `dw` here takes those
+two tensors and takes them BY KEYWORD ONLY: a reference-style positional call raises a TypeError instead
+of silently computing something else.  `layers/inv_conv.py` holds the backward that goes with it.
+`dy` returns the true input gradient L^-T g (the reference's dy computes L^-1 g).
 """
 from . import functional as F
 
@@ -33,10 +37,11 @@ def dy(grad_output, kernel, M=None, output=None, groups=None):
     return [F.bwd_input(grad_output, kernel, groups=groups, out=output)]
 
 
-def dw(saved_output, kernel, grad_input, M=None, output=None, groups=None):
+def dw(*, saved_output, kernel, grad_input, M=None, output=None, groups=None):
     """reference: dw(input, kernel, grad_output, M, output) -> [output]   (.cpp:99-112).
 
-    Here: `saved_output` = y of `inverse`, `grad_input` = dX returned by `dy`."""
+    Keyword-only on purpose (see the module docstring): `saved_output` = y returned by `inverse`,
+    `grad_input` = dX returned by `dy`."""
     return [F.bwd_weight(grad_input, saved_output, kernel, groups=groups, out=output)]
 
 

@@ -3,9 +3,13 @@
 Same class / function names, constructor signatures, parameter name (`weight_fwd`), return
 conventions ((out, 0.0) from forward, tensor from reverse) and helper methods as the
 reference (inv_conv.py:43-91 `inv_conv_`, `inv_conv_4d`; :94-364 `inv_flow_with_pad`;
-:365-513 `inv_flow_no_pad`), so `create_model` of the if_* experiments and reference
-checkpoints (state_dict key `weight_fwd`) work unchanged.  The compute goes through the C
-ABI (inverse_flow_b200.functional); there is no PyTorch fallback.
+:365-513 `inv_flow_no_pad`), so `create_model` of the if_* experiments works unchanged and
+reference checkpoints load (state_dict key `weight_fwd`).  Loaded weights mean the same operator
+for `inv_flow_no_pad` and order 'TL' -- the only variants the if_* models use; a reference checkpoint of
+a TR/BL/BR layer stores the weight in whatever flip state its last forward left it (the reference
+toggles `weight_fwd.data` on every call, inv_conv.py:198-214), while here `weight_fwd` is always the
+top-left kernel of the reflected frame.  The compute goes through the C ABI
+(inverse_flow_b200.functional); there is no PyTorch fallback.
 
 Deliberate differences, all documented in DESIGN.md:
   * backward returns the true gradients (dX = L^-T g, dW = -corr(dX, y)), SURVEY.md 0.4;

@@ -534,6 +534,120 @@ def test_reference_module_call_style():
     np.testing.assert_allclose(back[0].cpu().numpy(), x.cpu().numpy(), atol=1e-5)
     with pytest.raises(RuntimeError):
         inv_conv_with_bp.inverse(x.transpose(2, 3), w, out)        # CHECK_CONTIGUOUS
+    # the reference's backward calls dw(input_x, kernel, output_grad, M, out) (inv_conv.py:79): that argument
+    # order is not what the weight gradient depends on -- it must fail loudly, never compute something else
+    g = dev(rng.standard_normal((2, 4, 5, 5)))
+    with pytest.raises(TypeError):
+        inv_conv_with_bp.dw(x, w, g, None, torch.zeros_like(w))
+    dx = inv_conv_with_bp.dy(g, w, None, torch.zeros_like(g))[0]
+    dw = inv_conv_with_bp.dw(saved_output=z[0], kernel=w, grad_input=dx, output=torch.zeros_like(w))[0]
+    x64, w64, g64 = (t.cpu().numpy().astype(np.float64) for t in (x, w, g))
+    dx_ref, dw_ref = oracle.backward(g64, oracle.inverse(x64, w64, 4), w64, 4)
+    assert oracle.max_rel_err(dx.cpu().numpy(), dx_ref) < TOL and oracle.max_rel_err(dw.cpu().numpy(), dw_ref) < TOL
+
+
+def test_caller_allocated_outputs_are_validated(IF):
+    """a wrong-shaped, wrong-dtype or aliasing `out`, a channels_last activation, or prepared weights of another
+    kernel must raise -- never become an out-of-bounds device write"""
+    rng = np.random.default_rng(19)
+    x = dev(rng.standard_normal((3, 4, 6, 6)))
+    g = dev(rng.standard_normal((3, 4, 6, 6)))
+    w = dev(make_weight(rng, 4, 4, 3, 3))
+    y = IF.inverse(x, w, groups=1)
+    for bad in (torch.empty(3, 4, 6, 5, device="cuda"), torch.empty(3, 4, 6, 6, device="cuda", dtype=torch.float64),
+                torch.empty(3, 4, 6, 6)):
+        with pytest.raises((ValueError, RuntimeError)):
+            IF.bwd_input(g, w, groups=1, out=bad)
+        with pytest.raises((ValueError, RuntimeError)):
+            IF.inverse(x, w, groups=1, out=bad)
+    with pytest.raises(ValueError):
+        IF.bwd_input(g, w, groups=1, out=g)                        # aliasing
+    dx = IF.bwd_input(g, w, groups=1)
+    for bad in (torch.empty(4, 4, 3, 2, device="cuda"), torch.empty(4, 4, 3, 3, device="cuda", dtype=torch.float16)):
+        with pytest.raises((ValueError, RuntimeError)):
+            IF.bwd_weight(dx, y, w, groups=1, out=bad)
+    with pytest.raises(RuntimeError, match="channels_last"):
+        IF.inverse(x.contiguous(memory_format=torch.channels_last), w, groups=1)
+    other = IF.Prepared(dev(make_weight(rng, 4, 4, 2, 2)), 1)
+    with pytest.raises(ValueError):
+        IF.inverse(x, w, groups=1, prepared=other)
+
+
+def test_inverse_once_matches_prepare_then_inverse(IF):
+    """ifk_inverse_once_f32: the reference's one-call inverse(input, kernel, output) (inv_conv_with_bp_general.cpp:19-28)"""
+    import ctypes
+    from inverse_flow_b200 import _native
+    lib = _native.load()
+    rng = np.random.default_rng(20)
+    for (B, C, H, W, k, groups) in [(5, 12, 8, 8, 3, 1), (7, 4, 14, 14, 2, 4)]:
+        x = dev(rng.standard_normal((B, C, H, W)))
+        w = dev(make_weight(rng, C, C, k, k, 0.05))
+        p = _native.problem(B, C, H, W, k, k, C, groups)
+        scratch = torch.empty(lib.ifk_prepared_floats(ctypes.byref(p)), device="cuda")
+        y = torch.empty_like(x)
+        _native.check(lib.ifk_inverse_once_f32(ctypes.byref(p), x.data_ptr(), w.data_ptr(), scratch.data_ptr(), y.data_ptr(),
+                                               _native.current_stream(x.device)))
+        assert torch.equal(y, IF.inverse(x, w, groups=groups))
+
+
+CHAIN_CASES = [
+    # (B, C, H, W, k, groups), layer orientations
+    ((100, 12, 16, 16, 3, 1), ("TL", "TR", "BL", "BR")),          # Inv_FlowUnit at the imagenet32 / cifar level-1 shape
+    ((100, 24, 8, 8, 3, 1), ("TL", "TR", "BL", "BR")),
+    ((100, 48, 4, 4, 3, 1), ("TL", "TR", "BL", "BR")),
+    ((37, 48, 4, 4, 3, 4), ("BR", "TL", "TL", "BL", "TR")),
+    ((300, 12, 6, 6, 3, 1), ("TL", "BR", "TR")),                   # more images than CTAs: a stripe per CTA
+    ((5, 12, 5, 7, 3, 1), ("TL",) * 11),                           # more layers than one launch takes
+    ((4, 8, 7, 7, 2, 1), ("TL", "TR", "BL", "BR")),               # no resident chain kernel: served layer by layer
+]
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=lambda c: "x".join(map(str, c[0])) + "-" + "".join(c[1]))
+def test_inverse_chain_is_bit_identical_to_single_launches(IF, case):
+    """ifk_inverse_chain_f32: consecutive layers in one launch, the image never leaving shared memory -- every
+    layer's output bit-identical to the per-layer launches (and hence inside the oracle's tolerance)"""
+    (B, C, H, W, k, groups), orients = case
+    rng = np.random.default_rng(41)
+    x = dev(rng.standard_normal((B, C, H, W)))
+    ws = [dev(make_weight(rng, C, C, k, k, 0.03)) for _ in orients]
+    prepared = [IF.Prepared(w, groups) for w in ws]
+    ys = IF.inverse_chain(x, prepared, orients)
+    cur = x
+    for w, pr, o, y in zip(ws, prepared, orients, ys):
+        ref = IF.inverse(cur, w, prepared=pr, orient=o)
+        assert torch.equal(y, ref)
+        cur = ref
+    x64 = x[:3].cpu().numpy().astype(np.float64)
+    for w, o in zip(ws, orients):
+        x64 = oracle.inverse(x64, w.cpu().numpy().astype(np.float64), groups, orient=o)
+    assert oracle.max_rel_err(ys[-1][:3].cpu().numpy(), x64) < TOL
+
+
+def test_inv_flow_unit_is_one_chained_launch_with_the_layers_gradients():
+    """Inv_FlowUnit (reference inf/layers/inv_flow.py:28-53) = TL -> TR -> BL -> BR in one launch; outputs and all
+    gradients equal those of the four layers applied one after the other"""
+    from inverse_flow_b200.layers import Inv_FlowUnit
+    torch.manual_seed(3)
+    unit = Inv_FlowUnit(12, 12, (3, 3), groups=1).cuda()
+    x = torch.randn(9, 12, 16, 16, device="cuda", requires_grad=True)
+    g = torch.randn(9, 12, 16, 16, device="cuda")
+    y, ldj = unit(x)
+    y.backward(g)
+    got = [x.grad.clone()] + [c.weight_fwd.grad.clone() for c in unit._convs()]
+    x.grad = None
+    for c in unit._convs():
+        c.weight_fwd.grad = None
+    cur = x
+    for c in unit._convs():
+        cur, _ = c(cur)
+    cur.backward(g)
+    want = [x.grad] + [c.weight_fwd.grad for c in unit._convs()]
+    assert ldj == 0.0 and torch.equal(y, cur)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    # (round trip through four layers of the reference initialisation -- W[:, -1, -1, -1] = 1 makes each operator
+    #  amplify by an order of magnitude, |y| ~ 5e2 here -- so the reconstruction carries that conditioning)
+    assert oracle.max_rel_err(unit.reverse(y.detach()).cpu().numpy(), x.detach().cpu().numpy()) < 5e-3
 
 
 def test_runs_on_the_callers_stream_and_in_a_graph(IF):

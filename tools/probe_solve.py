@@ -28,6 +28,7 @@ def main():
     ap.add_argument("dims", type=int, nargs=6)
     ap.add_argument("--reverse", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--chain", type=int, default=0, help="also time N-layer chains (ifk_inverse_chain_f32, TL/TR/BL/BR)")
     args = ap.parse_args()
     B, C, H, W, k, g = args.dims
     lib = _native.load()
@@ -83,6 +84,47 @@ def main():
         e1.synchronize()
         best = min(best, e0.elapsed_time(e1) / reps * 1e3)
     print("  %.2f us per launch (%d chained launches in a graph)" % (best, reps))
+
+    if args.chain:
+        n = args.chain
+        orients = [("TL", "TR", "BL", "BR")[i % 4] for i in range(n)]
+        ws = [reference_init_weight(C, k).cuda() for _ in range(n)]
+        preps = [IF.Prepared(wi, g) for wi in ws]
+        outs = [torch.empty_like(x) for _ in range(n)]
+
+        def single():
+            cur = x
+            for pr, o, out_i in zip(preps, orients, outs):
+                q = _native.with_flags(pr.for_batch(cur, o), _native.FLAG_STABLE_PREPARED)
+                _native.check(lib.ifk_inverse_f32(ctypes.byref(q), cur.data_ptr(), pr.buffer.data_ptr(), out_i.data_ptr(),
+                                                  _native.current_stream(x.device)))
+                cur = out_i
+
+        def chained():
+            IF.inverse_chain(x, preps, orients, outs=outs)
+
+        res = {}
+        for name, fn in (("single launches", single), ("one chained launch", chained)):
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(16):
+                    fn()
+            for _ in range(3):
+                gr.replay()
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                gr.replay()
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1) / 16 * 1e3)
+            res[name] = best
+            print("  %d-layer unit, %s: %.2f us (%.2f us per layer)" % (n, name, best, best / n))
 
     if not args.no_parity:
         from oracle import oracle
