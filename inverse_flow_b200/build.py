@@ -14,7 +14,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libifk_b200.so")
-SOURCES = ["ifk_api.cu", "ifk_env.cu", "ifk_comm.cu", "ifk_microbench.cu", "ifk_solve_wave.cu", "ifk_prepare.cu", "ifk_solve.cu", "ifk_solve_v1.cu", "ifk_solve_v2.cu",
+SOURCES = ["ifk_api.cu", "ifk_env.cu", "ifk_comm.cu", "ifk_microbench.cu", "ifk_solve_wave.cu", "ifk_solve_split.cu", "ifk_prepare.cu", "ifk_solve.cu", "ifk_solve_v1.cu", "ifk_solve_v2.cu",
            "ifk_solve_v4.cu", "ifk_solve_stream.cu", "ifk_solve_window.cu", "ifk_solve_shfl.cu", "ifk_conv.cu", "ifk_bwd_weight.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -32,6 +32,7 @@ static void parse_env()
     k.solve_window = is_one("IFK_SOLVE_WINDOW");
     k.shfl_off = is_zero("IFK_SOLVE_SHFL");
     k.wave_off = is_zero("IFK_SOLVE_WAVE");
+    k.split_off = !is_one("IFK_SOLVE_SPLIT");     // opt-in: measured slower than the wave kernel
     k.nobulk = is_one("IFK_SOLVE_NOBULK");
     k.dw_quad_off = is_zero("IFK_DW_QUAD");
     k.pdl = !is_zero("IFK_PDL");
@@ -46,6 +47,7 @@ static void parse_env()
         sscanf(e, "%d,%d,%d,%d", &k.window_cfg[0], &k.window_cfg[1], &k.window_cfg[2], &k.window_cfg[3]);
     if (const char *e = getenv("IFK_WAVE_CFG"))
         sscanf(e, "%d,%d,%d,%d", &k.wave_cfg[0], &k.wave_cfg[1], &k.wave_cfg[2], &k.wave_cfg[3]);
+    if (const char *e = getenv("IFK_SPLIT_CFG")) sscanf(e, "%d,%d", &k.split_cfg[0], &k.split_cfg[1]);
     std::lock_guard<std::mutex> lock(g_env_mutex);
     g_env = k;
     g_env_generation++;

@@ -11,6 +11,7 @@ struct EnvKnobs {
     bool solve_window;   // IFK_SOLVE_WINDOW=1  : the window kernel
     bool shfl_off;       // IFK_SOLVE_SHFL=0    : no shuffle kernel
     bool wave_off;       // IFK_SOLVE_WAVE=0    : no pipelined wavefront kernel (-> the older resident kernel)
+    bool split_off;      // IFK_SOLVE_SPLIT=1 switches the warp-specialised wavefront kernel ON (default: the wave kernel)
     bool nobulk;         // IFK_SOLVE_NOBULK=1  : no TMA bulk staging
     bool dw_quad_off;    // IFK_DW_QUAD=0       : dW stage 1 by the per-tap kernel also where the quad kernel applies
     bool pdl;            // IFK_PDL=0 switches programmatic dependent launch off
@@ -21,6 +22,7 @@ struct EnvKnobs {
     int stream_cfg[2];   // IFK_STREAM_CFG="cc,nv"          (0 = unset)
     int window_cfg[4];   // IFK_WINDOW_CFG="cc,nv,cs,rp"    (0 = unset)
     int wave_cfg[4];     // IFK_WAVE_CFG="cc,ns,vec,threads" (0 = unset) : tuning
+    int split_cfg[2];    // IFK_SPLIT_CFG="nsh"            (0 = unset) : tuning
     bool pins_other_solver() const { return solve_global || solve_stream || solve_window || has_solve_cfg; }
 };
 

@@ -60,6 +60,15 @@ int describe_wave_solve(const Geometry &g, char *buf, size_t buflen);
 int launch_solve_wave(const Geometry &g, const float *in, const float *prepared, float *out, bool reverse,
                       int flags, long long *probe, cudaStream_t s);
 
+bool split_solve_available(const Geometry &g);
+int describe_split_solve(const Geometry &g, char *buf, size_t buflen);
+size_t split_pack_floats(const Geometry &g);                    // per layer, floats
+size_t split_pack_offset(const Geometry &g);                    // floats from the start of a layer's prepared buffer
+int launch_split_pack(const Geometry &g, const float *prepared, float *pack, int count, size_t prepared_stride,
+                      cudaStream_t s);
+int launch_split_layers(const Geometry &g, int n, const int *orients, const float *const *packs, const float *in,
+                        float *const *outs, bool reverse, int flags, long long *probe, cudaStream_t s);
+
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 
 }  // namespace ifk

@@ -244,6 +244,10 @@ int launch_solve(const Geometry &g, const float *in, const float *prepared, floa
     if (g.B == 0) return 0;
     const float *prep_dir = prepared_dir(g, prepared, reverse ? 1 : 0);
     if (shfl_solve_available(g)) return launch_solve_shfl(g, in, prep_dir, out, reverse, probe, s);
+    if (split_solve_available(g)) {
+        const float *pack = prepared + split_pack_offset(g);
+        return launch_split_layers(g, 1, nullptr, &pack, in, &out, reverse, g.flags, probe, s);
+    }
     if (wave_solve_available(g)) return launch_solve_wave(g, in, prepared, out, reverse, g.flags, probe, s);
     const SolveConfig c = choose_config(g);
     SolveParams p{};
@@ -281,6 +285,7 @@ int launch_solve(const Geometry &g, const float *in, const float *prepared, floa
 int describe_solve(const Geometry &g, char *buf, size_t buflen)
 {
     if (shfl_solve_available(g)) return describe_shfl_solve(g, buf, buflen);
+    if (split_solve_available(g)) return describe_split_solve(g, buf, buflen);
     if (wave_solve_available(g)) return describe_wave_solve(g, buf, buflen);
     const SolveConfig c = choose_config(g);
     if (c.smem)

@@ -174,8 +174,8 @@ solve_wave_kernel(const WaveParams p)
             mbar_expect_tx(bar, img_bytes);
             bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
         }
-        smem[2] = 0.f;          // source of the opaque zero used by Hold
     }
+    if (tid == 0) smem[2] = 0.f;          // source of the opaque zero used by Hold
     if (!p.early) { load_weights(0); load_offsets(); }
     // zero halo (and the extra column the look-ahead touches): once per CTA -- the interior of xh is
     // rewritten for every image, the interior of yb is written before it is read
@@ -638,13 +638,17 @@ size_t prepared_floats(const Geometry &g)
         const WavePackDims d = wave_pack_dims(*v, g.groups);
         n += d.pack_floats + d.code_ints;
     }
-    return n;
+    return n + split_pack_floats(g);                          // the split kernel's packed copy comes last
 }
+
+size_t split_pack_offset(const Geometry &g) { return prepared_floats(g) - split_pack_floats(g); }
 
 int launch_wave_pack(const Geometry &g, float *prepared, int count, size_t prepared_stride, cudaStream_t s)
 {
+    if (count <= 0) return 0;
+    if (int st = launch_split_pack(g, prepared, prepared + split_pack_offset(g), count, prepared_stride, s)) return st;
     const WaveVariant *v = wave_family(g);
-    if (!v || count <= 0) return 0;
+    if (!v) return 0;
     const WavePackDims d = wave_pack_dims(*v, g.groups);
     WavePackParams q{};
     q.prepared = prepared;
@@ -741,6 +745,19 @@ int launch_solve_chain(const Geometry &g, int n, const int *orients, const float
                        float *const *ys, cudaStream_t s)
 {
     if (g.B == 0) return 0;
+    if (split_solve_available(g)) {
+        const size_t off = split_pack_offset(g);
+        const float *in = x;
+        for (int i = 0; i < n; i += kWaveChainMax) {
+            const int m = n - i < kWaveChainMax ? n - i : kWaveChainMax;
+            const float *packs[kWaveChainMax];
+            for (int k = 0; k < m; k++) packs[k] = prepared[i + k] + off;
+            const int st = launch_split_layers(g, m, orients + i, packs, in, ys + i, false, 0, nullptr, s);
+            if (st != 0) return st;
+            in = ys[i + m - 1];
+        }
+        return 0;
+    }
     if (!choose_wave(g).ok) return IFK_ERR_UNSUPPORTED;
     const float *in = x;
     for (int i = 0; i < n; i += kWaveChainMax) {

@@ -102,7 +102,8 @@ def test_describe_solve_picks_the_on_chip_kernels_for_model_shapes(lib, monkeypa
     """model shapes stay on chip: the register/shuffle kernel where one warp's lanes cover the rows
     and a lane can hold its weights (MNIST-sized layers), the shared-memory resident kernel otherwise"""
     for shape, kind in [((100, 4, 14, 14, 2), "shfl<"), ((100, 8, 7, 7, 2), "shfl<"), ((64, 1, 28, 28, 3), "shfl<"),
-                        ((100, 12, 16, 16, 3), "wave<"), ((100, 24, 8, 8, 3), "wave<"), ((100, 48, 4, 4, 3), "wave<")]:
+                        ((100, 12, 16, 16, 3), "wave<"), ((100, 24, 8, 8, 3), "wave<"), ((100, 48, 4, 4, 3), "wave<"),
+                        ((100, 12, 32, 32, 3), "wave<")]:
         B, C, H, W, k = shape
         d = _native.describe_solve(_native.problem(B, C, H, W, k, k, C, 1))
         assert d.startswith(kind), (shape, d)
@@ -164,7 +165,7 @@ def test_kernel_selection_is_well_formed_over_the_sweep_grid(lib):
                         d = _native.describe_solve(p)
                         kind = d.split("<")[0].split(" ")[0]
                         kinds[kind] = kinds.get(kind, 0) + 1
-                        assert kind in ("shfl", "wave", "smem", "window", "stream", "global"), d
+                        assert kind in ("shfl", "split", "wave", "smem", "window", "stream", "global"), d
                         m = re.search(r"smem=(\d+)B", d)
                         if m:
                             assert int(m.group(1)) <= 227 * 1024, d

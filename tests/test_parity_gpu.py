@@ -162,7 +162,7 @@ ORIENT_SHAPES = [(3, 12, 16, 16, 3, 3, 1, 0.02), (2, 8, 7, 7, 2, 2, 4, 0.05), (2
                  (3, 20, 10, 10, 3, 3, 1, 0.02)]
 
 
-@pytest.mark.parametrize("kernel", ["default", "wave", "resident", "window", "stream", "global"])
+@pytest.mark.parametrize("kernel", ["default", "split", "wave", "resident", "window", "stream", "global"])
 @pytest.mark.parametrize("orient", ["TR", "BL", "BR"])
 @pytest.mark.parametrize("shape", ORIENT_SHAPES, ids=lambda s: "x".join(map(str, s[:7])))
 def test_orientations_by_index_reflection(IF, shape, orient, kernel, monkeypatch):
@@ -182,6 +182,11 @@ def test_orientations_by_index_reflection(IF, shape, orient, kernel, monkeypatch
         from inverse_flow_b200 import _native
         if not _native.describe_solve(_native.problem(*shape[:6], shape[1], shape[6])).startswith("wave<"):
             pytest.skip("no pipelined wavefront variant for this group width / kernel size")
+    elif kernel == "split":
+        from inverse_flow_b200 import _native
+        monkeypatch.setenv("IFK_SOLVE_SPLIT", "1")      # opt-in kernel
+        if not _native.describe_solve(_native.problem(*shape[:6], shape[1], shape[6])).startswith("split<"):
+            pytest.skip("no warp-specialised variant for this group width / kernel size / image height")
     elif kernel == "global":
         monkeypatch.setenv("IFK_SOLVE_GLOBAL", "1")
     B, C, H, W, KH, KW, groups, scale = shape
@@ -223,6 +228,44 @@ def test_wave_kernel(IF, case, monkeypatch):
         cc, ns, vec = family.split(",")
         assert "cc=%s,ns=%s,vec=%s" % (cc, ns, vec) in d, d
     rng = np.random.default_rng(29)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = make_weight(rng, C, C, KH, KW, scale)
+    assert_parity(run_all(IF, x, w, g, groups))
+    for orient in ("TR", "BL", "BR"):
+        assert_parity(run_all(IF, x[:5], w, g[:5], groups, orient=orient))
+    monkeypatch.setenv("IFK_SOLVE_NOBULK", "1")
+    assert_parity(run_all(IF, x[:3], w, g[:3], groups))
+
+
+# (B, C, H, W, KH, KW, groups, tap scale) x reduction split of the helper warps (None = the default family)
+SPLIT_CASES = [
+    ((100, 12, 16, 16, 3, 3, 1, 0.02), None), ((100, 12, 16, 16, 3, 3, 1, 0.02), "8"),          # imagenet32 level 1
+    ((256, 12, 16, 16, 3, 3, 1, 0.02), None), ((256, 12, 16, 16, 3, 3, 1, 0.02), "8"),          # cifar batch
+    ((100, 24, 8, 8, 3, 3, 1, 0.02), None), ((256, 24, 8, 8, 3, 3, 1, 0.02), None),
+    ((100, 48, 4, 4, 3, 3, 4, 0.02), None), ((301, 48, 4, 4, 3, 3, 4, 0.02), None),             # reference's 4 groups: Cg = 12
+    ((5, 12, 5, 7, 3, 3, 1, 0.05), None), ((5, 12, 7, 5, 3, 3, 1, 0.05), "8"),                  # ragged
+    ((2, 12, 16, 9, 3, 3, 1, 0.02), None), ((7, 24, 5, 11, 3, 3, 1, 0.02), None), ((2, 24, 8, 30, 3, 3, 1, 0.02), None),
+    ((300, 12, 6, 6, 3, 3, 1, 0.02), None),                                                    # stripes of images per CTA
+    ((3, 12, 2, 2, 3, 3, 1, 0.05), None), ((3, 12, 1, 9, 3, 3, 1, 0.05), None), ((3, 12, 16, 40, 3, 3, 1, 0.02), None),
+]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES, ids=lambda c: "x".join(map(str, c[0][:7])) + ("-" + c[1] if c[1] else ""))
+def test_split_kernel(IF, case, monkeypatch):
+    """the warp-specialised wavefront kernel (ifk_solve_split.cu): every compiled family, BASELINE batches,
+    ragged images, batches beyond the grid, all orientations, with and without TMA"""
+    from inverse_flow_b200 import _native
+    shape, family = case
+    monkeypatch.setenv("IFK_SOLVE_SPLIT", "1")          # opt-in kernel
+    if family:
+        monkeypatch.setenv("IFK_SPLIT_CFG", family)
+    B, C, H, W, KH, KW, groups, scale = shape
+    d = _native.describe_solve(_native.problem(B, C, H, W, KH, KW, C, groups))
+    assert d.startswith("split<"), d
+    if family:
+        assert "ns=%s," % family in d, d
+    rng = np.random.default_rng(37)
     x = rng.standard_normal((B, C, H, W)).astype(np.float32)
     g = rng.standard_normal((B, C, H, W)).astype(np.float32)
     w = make_weight(rng, C, C, KH, KW, scale)
