@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define IFK_VERSION 300 /* major*10000 + minor*100 + patch */
+#define IFK_VERSION 400 /* major*10000 + minor*100 + patch */
 
 /* cudaStream_t without the CUDA headers (a driver-level CUstream handle). */
 typedef struct CUstream_st *ifk_stream_t;
@@ -175,6 +175,29 @@ int ifk_inverse_once_f32(const ifk_problem *p, const float *x, const float *weig
  * (callers then issue the n calls). */
 int ifk_inverse_chain_f32(const ifk_problem *p, int n, const int *orients, const float *const *prepared,
                           const float *x, float *const *ys, ifk_stream_t stream);
+
+/* ---- elementwise neighbours fused into a solve's load and store ------------
+ * In the if_* Glow models every inverse-conv layer is preceded by an ActNorm affine and every block is
+ * opened by a Squeeze (model order: inf/experiments/if_glow_mnist.py:62-124; ActNorm.forward
+ * `(x - translation) * exp(-log_scale)`, inf/layers/actnorm.py:36; space_to_depth, inf/layers/squeeze.py:5-13).
+ * Both are pure re-indexing / per-channel FMAs: the solve kernels apply them while the image moves between
+ * global and shared memory, which removes two elementwise kernels (and their HBM round trips) per layer.
+ *   ifk_inverse_fused_f32   : y  = L^-1( in_scale (.) S(x) + in_bias )
+ *   ifk_bwd_input_fused_f32 : dx = L^-T g  (raw, what ifk_bwd_weight_f32 needs; may be NULL)
+ *                             dz = S^T( out_scale (.) dx )   (the gradient handed to the layer before)
+ * with S = space_to_depth when `squeeze` is set (x and dz are then (B, C/4, 2H, 2W) tensors; needs
+ * (C/groups) % 4 == 0) and the identity otherwise.  Scale / bias vectors have C floats; NULL = 1 / 0.
+ * IFK_ERR_UNSUPPORTED when the geometry is not served by the pipelined wavefront kernel (callers then run
+ * the unfused sequence). */
+typedef struct ifk_fused {
+    const float *in_scale, *in_bias; /* forward: per-channel affine of the (squeezed) input        */
+    const float *out_scale;          /* backward: per-channel scale of dz                           */
+    int squeeze;                     /* 0 / 1                                                       */
+} ifk_fused;
+int ifk_inverse_fused_f32(const ifk_problem *p, const ifk_fused *f, const float *x, const float *prepared,
+                          float *y, ifk_stream_t stream);
+int ifk_bwd_input_fused_f32(const ifk_problem *p, const ifk_fused *f, const float *g, const float *prepared,
+                            float *dx, float *dz, ifk_stream_t stream);
 
 /* Phase timing of ONE solve (a debugging / measuring entry point, not part of the product path):
  * like ifk_inverse_f32, and thread 0 of CTA (0,0) writes clock64() stamps into `probe` (16 x int64

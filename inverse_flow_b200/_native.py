@@ -21,7 +21,7 @@ EXPORTS = (
     "ifk_bwd_weight_f32", "ifk_bwd_weight_partial_f32", "ifk_bwd_weight_reduce_many_f32",
     "ifk_backward_f32", "ifk_describe_solve", "ifk_inverse_once_f32", "ifk_inverse_chain_f32",
     "ifk_inverse_probe_f32", "ifk_debug_reload_env", "ifk_debug_fp32_peak", "ifk_debug_latencies",
-    "ifk_allreduce_flag_bytes", "ifk_allreduce_peer_f32",
+    "ifk_allreduce_flag_bytes", "ifk_allreduce_peer_f32", "ifk_inverse_fused_f32", "ifk_bwd_input_fused_f32",
 )
 
 FLAG_STABLE_PREPARED = 1        # enum ifk_flags
@@ -32,6 +32,12 @@ ERR_UNSUPPORTED = -4
 class Problem(ctypes.Structure):
     """struct ifk_problem"""
     _fields_ = [(n, ctypes.c_int) for n in ("B", "C", "H", "W", "KH", "KW", "Cw", "groups", "orient", "flags")]
+
+
+class Fused(ctypes.Structure):
+    """struct ifk_fused: the ActNorm affine / Squeeze re-indexing fused into a solve's load and store"""
+    _fields_ = [("in_scale", ctypes.c_void_p), ("in_bias", ctypes.c_void_p), ("out_scale", ctypes.c_void_p),
+                ("squeeze", ctypes.c_int)]
 
 
 class IfkError(RuntimeError):
@@ -78,6 +84,10 @@ def load():
     lib.ifk_inverse_chain_f32.argtypes = [P, ci, ctypes.POINTER(ci), ctypes.POINTER(vp), vp, ctypes.POINTER(vp), vp]
     lib.ifk_inverse_probe_f32.restype = ci
     lib.ifk_inverse_probe_f32.argtypes = [P, vp, vp, vp, vp, vp]
+    lib.ifk_inverse_fused_f32.restype = ci
+    lib.ifk_inverse_fused_f32.argtypes = [P, ctypes.POINTER(Fused), vp, vp, vp, vp]
+    lib.ifk_bwd_input_fused_f32.restype = ci
+    lib.ifk_bwd_input_fused_f32.argtypes = [P, ctypes.POINTER(Fused), vp, vp, vp, vp, vp]
     lib.ifk_debug_reload_env.restype = None
     lib.ifk_debug_reload_env.argtypes = []
     lib.ifk_allreduce_flag_bytes.restype = sz

@@ -190,6 +190,39 @@ int ifk_inverse_chain_f32(const ifk_problem *p, int n, const int *orients, const
     return launch_solve_chain(g, n, orients, prepared, x, ys, (cudaStream_t)stream);
 }
 
+static int check_fused(const Geometry &g, const ifk_fused *f)
+{
+    if (!f) return IFK_ERR_NULL_POINTER;
+    if (f->squeeze != 0 && f->squeeze != 1) return IFK_ERR_BAD_FLAGS;
+    if (f->squeeze && g.Cg % 4 != 0) return IFK_ERR_BAD_SHAPE;
+    if (!wave_solve_available(g)) return IFK_ERR_UNSUPPORTED;
+    return IFK_OK;
+}
+
+int ifk_inverse_fused_f32(const ifk_problem *p, const ifk_fused *f, const float *x, const float *prepared, float *y,
+                          ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if ((st = check_fused(g, f)) != IFK_OK) return st;
+    if (!prepared || (g.B > 0 && (!x || !y))) return IFK_ERR_NULL_POINTER;
+    if (g.B == 0) return IFK_OK;
+    return launch_solve_wave_fused(g, *f, x, prepared, y, nullptr, false, (cudaStream_t)stream);
+}
+
+int ifk_bwd_input_fused_f32(const ifk_problem *p, const ifk_fused *f, const float *grad, const float *prepared,
+                            float *dx, float *dz, ifk_stream_t stream)
+{
+    Geometry g;
+    int st = make_geometry(p, &g);
+    if (st != IFK_OK) return st;
+    if ((st = check_fused(g, f)) != IFK_OK) return st;
+    if (!prepared || (g.B > 0 && (!grad || !dz))) return IFK_ERR_NULL_POINTER;
+    if (g.B == 0) return IFK_OK;
+    return launch_solve_wave_fused(g, *f, grad, prepared, dx, dz, true, (cudaStream_t)stream);
+}
+
 // Measuring aid (ifk.h): one solve whose CTA (0,0) stamps clock64() at its phase boundaries.
 int ifk_inverse_probe_f32(const ifk_problem *p, const float *x, const float *prepared, float *y,
                           long long *probe, ifk_stream_t stream)

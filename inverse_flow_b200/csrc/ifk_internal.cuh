@@ -59,6 +59,9 @@ bool wave_solve_available(const Geometry &g);
 int describe_wave_solve(const Geometry &g, char *buf, size_t buflen);
 int launch_solve_wave(const Geometry &g, const float *in, const float *prepared, float *out, bool reverse,
                       int flags, long long *probe, cudaStream_t s);
+// fused neighbours (ifk.h: ifk_fused); out may be nullptr when out2 is given
+int launch_solve_wave_fused(const Geometry &g, const ifk_fused &f, const float *in, const float *prepared, float *out,
+                            float *out2, bool reverse, cudaStream_t s);
 
 bool split_solve_available(const Geometry &g);
 int describe_split_solve(const Geometry &g, char *buf, size_t buflen);

@@ -50,6 +50,12 @@ struct WaveParams {
     unsigned mW;        // ceil(2^32 / W): m / W == umulhi(m, mW) for every pixel index
     int tm_shift;       // log2 of the pixel lanes of the transposing passes (a power of two dividing the threads)
     long long *probe;   // clock64() stamps of CTA (0,0) thread 0 (ifk_inverse_probe_f32), or nullptr
+    // fused neighbours (ifk.h: ifk_fused; single-layer launches only)
+    const float *in_scale, *in_bias;   // per-channel affine applied while the image is transposed into xh
+    const float *out_scale;            // per-channel scale of the second output
+    float *out2;                       // second output (scaled, un-squeezed), or nullptr
+    int squeeze_in, squeeze_out;       // the input / the second output is a (C/4, 2H, 2W) image
+    int fused;                         // any of the above
 };
 
 // reduce-scatter of N per-lane partial sums over M adjacent lanes (compile-time recursive halving,
@@ -228,6 +234,28 @@ solve_wave_kernel(const WaveParams p)
             float *d = xh + ((h + KH - 1) * RSP + (w + KW - 1) * PS) + tc * VEC;
             const float *sp = xbuf + m + tc * VEC * HW;
             const int dstep = TC * VEC, sstep = TC * VEC * HW;
+            if (VEC == 2 && p.fused) {
+                // the ActNorm affine and the Squeeze re-indexing ride on this pass: squeezed channel c = 4 c0 + 2 i + j
+                // of pixel (hm, wm) is element (c0, 2 hm + i, 2 wm + j) of the (C/4, 2H, 2W) image -- a channel PAIR is
+                // two adjacent floats of it
+                const float *sc = p.in_scale ? p.in_scale + G * CG : nullptr;
+                const float *bi = p.in_bias ? p.in_bias + G * CG : nullptr;
+                for (int cv = tc; cv < CGV; cv += TC, d += dstep, sp += sstep) {
+                    const int c = cv * 2;
+                    float v0, v1;
+                    if (p.squeeze_in) {
+                        const float2 t2 = *reinterpret_cast<const float2 *>(
+                            xbuf + (c >> 2) * 4 * HW + (2 * hm + ((c >> 1) & 1)) * 2 * W + 2 * wm);
+                        v0 = t2.x; v1 = t2.y;
+                    } else {
+                        v0 = sp[0]; v1 = sp[HW];
+                    }
+                    if (sc) { v0 *= __ldg(sc + c); v1 *= __ldg(sc + c + 1); }
+                    if (bi) { v0 += __ldg(bi + c); v1 += __ldg(bi + c + 1); }
+                    *reinterpret_cast<float2 *>(d) = make_float2(v0, v1);
+                }
+                continue;
+            }
 #pragma unroll 2
             for (int cv = tc; cv < CGV; cv += TC, d += dstep, sp += sstep) {
                 if (VEC == 4) *reinterpret_cast<float4 *>(d) = make_float4(sp[0], sp[HW], sp[2 * HW], sp[3 * HW]);
@@ -329,6 +357,26 @@ solve_wave_kernel(const WaveParams p)
             float *xn = xh + ((h2 + KH - 1) * RSP + (w2 + KW - 1) * PS) + tc * VEC;
             float *d = dst + m + tc * VEC * HW;
             const int sstep = TC * VEC, dstep = TC * VEC * HW;
+            if (VEC == 2 && p.fused) {
+                // the adjoint of the fused neighbours: raw result to `out` (dW reads it), per-channel scaled and
+                // un-squeezed (depth_to_space) to `out2`
+                const float *os = p.out_scale ? p.out_scale + G * CG : nullptr;
+                float *dst2 = p.out2 ? p.out2 + (size_t)G * CG * HW + (size_t)b * img_stride : nullptr;
+                for (int cv = tc; cv < CGV; cv += TC, sp += sstep, d += dstep) {
+                    const float2 t2 = *reinterpret_cast<const float2 *>(sp);
+                    if (p.out[li]) { d[0] = t2.x; d[HW] = t2.y; }
+                    if (dst2) {
+                        const int c = cv * 2;
+                        float v0 = t2.x, v1 = t2.y;
+                        if (os) { v0 *= __ldg(os + c); v1 *= __ldg(os + c + 1); }
+                        if (p.squeeze_out)
+                            *reinterpret_cast<float2 *>(dst2 + (c >> 2) * 4 * HW + (2 * hm + ((c >> 1) & 1)) * 2 * W + 2 * wm) =
+                                make_float2(v0, v1);
+                        else { dst2[c * HW + m] = v0; dst2[(c + 1) * HW + m] = v1; }
+                    }
+                }
+                continue;
+            }
 #pragma unroll 2
             for (int cv = tc; cv < CGV; cv += TC, sp += sstep, xn += sstep, d += dstep) {
                 if (VEC == 4) {
@@ -433,7 +481,10 @@ wave_pack_kernel(const WavePackParams q)
     X(24, 3, 3, 6, 16, 2, 2, 256) X(24, 3, 3, 6, 16, 2, 4, 256)                                      \
     X(48, 3, 3, 6, 16, 2, 2, 256)                                                                    \
     X(48, 3, 3, 6, 32, 2, 4, 256)                                                                    \
-    X(6, 3, 3, 6, 4, 2, 1, 256) X(6, 3, 3, 6, 4, 2, 2, 256)
+    X(6, 3, 3, 6, 4, 2, 1, 256) X(6, 3, 3, 6, 4, 2, 2, 256)                                          \
+    X(12, 3, 3, 3, 2, 2, 1, 128) X(12, 3, 3, 3, 2, 2, 2, 128)                                        \
+    X(24, 3, 3, 3, 4, 2, 1, 256) X(24, 3, 3, 3, 4, 2, 2, 256)                                        \
+    X(48, 3, 3, 3, 8, 2, 2, 256)
 
 struct WaveVariant {
     int cg, kh, kw, cc, ns, vec, iters, nthr;
@@ -667,10 +718,12 @@ int launch_wave_pack(const Geometry &g, float *prepared, int count, size_t prepa
 
 // one launch over `n` consecutive layers (n == 1: a plain solve).  prepared[i]: layer i's whole prepared buffer.
 static int launch_wave_layers(const Geometry &g, int n, const int *orients, const float *const *prepared, const float *in,
-                              float *const *outs, bool reverse, int flags, long long *probe, cudaStream_t s)
+                              float *const *outs, bool reverse, int flags, long long *probe, cudaStream_t s,
+                              const ifk_fused *fused = nullptr, float *out2 = nullptr)
 {
     const WaveConfig c = choose_wave(g);
     if (!c.ok || n < 1 || n > kWaveChainMax) return IFK_ERR_UNSUPPORTED;
+    if (fused && (n != 1 || c.v.vec != 2)) return IFK_ERR_UNSUPPORTED;
     const WavePackDims d = wave_pack_dims(c.v, g.groups);
     WaveParams p{};
     p.in = in;
@@ -699,6 +752,16 @@ static int launch_wave_layers(const Geometry &g, int n, const int *orients, cons
         p.tm_shift = sh;
     }
     p.probe = probe;
+    if (fused) {
+        p.in_scale = reverse ? nullptr : fused->in_scale;
+        p.in_bias = reverse ? nullptr : fused->in_bias;
+        p.out_scale = reverse ? fused->out_scale : nullptr;
+        p.out2 = reverse ? out2 : nullptr;
+        p.squeeze_in = reverse ? 0 : fused->squeeze;
+        p.squeeze_out = reverse ? fused->squeeze : 0;
+        p.fused = 1;
+        if (fused->squeeze && (((uintptr_t)in | (uintptr_t)out2) % 8 != 0)) return IFK_ERR_UNSUPPORTED;   // channel pairs move as float2
+    }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(c.threads);
     cfg.dynamicSmemBytes = c.smem_bytes;
@@ -738,6 +801,12 @@ int launch_solve_wave(const Geometry &g, const float *in, const float *prepared,
                       int flags, long long *probe, cudaStream_t s)
 {
     return launch_wave_layers(g, 1, nullptr, &prepared, in, &out, reverse, flags, probe, s);
+}
+
+int launch_solve_wave_fused(const Geometry &g, const ifk_fused &f, const float *in, const float *prepared, float *out,
+                            float *out2, bool reverse, cudaStream_t s)
+{
+    return launch_wave_layers(g, 1, nullptr, &prepared, in, &out, reverse, g.flags, nullptr, s, &f, out2);
 }
 
 // consecutive layers feeding each other (ifk_inverse_chain_f32): groups of up to kWaveChainMax layers per launch

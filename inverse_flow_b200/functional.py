@@ -243,3 +243,93 @@ def backward(grad, y, weight, groups=None, prepared=None, orient=0):
                                            _ptr(dx), _ptr(dw), _ptr(ws),
                                            _native.current_stream(grad.device)))
     return dx, dw
+
+
+# ---- elementwise neighbours fused into the solve (ifk.h: ifk_fused) ------------------
+def _check_vec(v, C, device, name):
+    if v is None:
+        return None
+    if not (isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 and v.dim() == 1 and
+            v.numel() == C and v.is_contiguous() and v.device == device):
+        raise ValueError("%s must be a contiguous float32 CUDA vector of %d entries on %s" % (name, C, device))
+    return v
+
+
+def space_to_depth(x):
+    """reference inf/layers/squeeze.py:5-13 (used by the unfused path and the tests)"""
+    B, C, H, W = x.shape
+    return x.view(B, C, H // 2, 2, W // 2, 2).permute(0, 1, 3, 5, 2, 4).contiguous().view(B, C * 4, H // 2, W // 2)
+
+
+def depth_to_space(x):
+    """reference inf/layers/squeeze.py:16-24"""
+    B, C, H, W = x.shape
+    return x.view(B, C // 4, 2, 2, H, W).permute(0, 1, 4, 2, 5, 3).contiguous().view(B, C // 4, H * 2, W * 2)
+
+
+def inverse_fused(x, weight, in_scale=None, in_bias=None, squeeze=False, groups=None, out=None, prepared=None, orient=0):
+    """y = L^-1( in_scale (.) S(x) + in_bias ): the ActNorm affine (reference inf/layers/actnorm.py:36) and, with
+    `squeeze`, the Squeeze re-indexing S = space_to_depth (inf/layers/squeeze.py:5-13; x is then the
+    (B, C/4, 2H, 2W) tensor) applied while the image enters shared memory -- one launch (ifk_inverse_fused_f32).
+    Geometries the pipelined wavefront kernel does not serve run the same composition unfused."""
+    lib = _native.load()
+    if prepared is None:
+        prepared = Prepared(weight, groups)
+    else:
+        prepared.check_weight(weight)
+    _check_activation(x, "input")
+    C = prepared.weight_shape[0]
+    B = x.shape[0]
+    if squeeze:
+        if x.shape[1] * 4 != C or x.shape[2] % 2 or x.shape[3] % 2:
+            raise ValueError("squeeze: input %s does not squeeze to %d channels" % (tuple(x.shape), C))
+        H, W = x.shape[2] // 2, x.shape[3] // 2
+    else:
+        H, W = x.shape[2], x.shape[3]
+    in_scale = _check_vec(in_scale, C, x.device, "in_scale")
+    in_bias = _check_vec(in_bias, C, x.device, "in_bias")
+    KH, KW = prepared.weight_shape[2:]
+    p = _native.problem(B, C, H, W, KH, KW, prepared.weight_shape[1], prepared.groups, orient)
+    if out is None:
+        out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+    f = _native.Fused(in_scale.data_ptr() if in_scale is not None else None,
+                      in_bias.data_ptr() if in_bias is not None else None, None, 1 if squeeze else 0)
+    with torch.cuda.device(x.device):
+        status = lib.ifk_inverse_fused_f32(ctypes.byref(p), ctypes.byref(f), _ptr(x), _ptr(prepared.buffer), _ptr(out),
+                                           _native.current_stream(x.device))
+        if status == _native.ERR_UNSUPPORTED or (squeeze and status == -2):
+            xs = space_to_depth(x) if squeeze else x                  # the unfused sequence, same kernels
+            if in_scale is not None:
+                xs = xs * in_scale.view(1, C, 1, 1)
+            if in_bias is not None:
+                xs = xs + in_bias.view(1, C, 1, 1)
+            return inverse(xs.contiguous(), weight, out=out, prepared=prepared, orient=orient)
+        _native.check(status)
+    return out
+
+
+def bwd_input_fused(grad, weight, out_scale=None, squeeze=False, groups=None, prepared=None, orient=0, want_dx=True):
+    """(dx, dz): dx = L^-T grad (raw: what bwd_weight reads) and dz = S^T( out_scale (.) dx ), the gradient handed to
+    the layer in front of the fused ActNorm / Squeeze -- one launch (ifk_bwd_input_fused_f32)."""
+    lib = _native.load()
+    if prepared is None:
+        prepared = Prepared(weight, groups)
+    else:
+        prepared.check_weight(weight)
+    _check_activation(grad, "grad_output")
+    B, C, H, W = grad.shape
+    out_scale = _check_vec(out_scale, C, grad.device, "out_scale")
+    p = prepared.for_batch(grad, orient)
+    dx = torch.empty_like(grad) if want_dx else None
+    dz = torch.empty((B, C // 4, 2 * H, 2 * W) if squeeze else (B, C, H, W), dtype=torch.float32, device=grad.device)
+    f = _native.Fused(None, None, out_scale.data_ptr() if out_scale is not None else None, 1 if squeeze else 0)
+    with torch.cuda.device(grad.device):
+        status = lib.ifk_bwd_input_fused_f32(ctypes.byref(p), ctypes.byref(f), _ptr(grad), _ptr(prepared.buffer),
+                                             _ptr(dx) if dx is not None else None, _ptr(dz),
+                                             _native.current_stream(grad.device))
+        if status == _native.ERR_UNSUPPORTED or (squeeze and status == -2):
+            dx = bwd_input(grad, weight, prepared=prepared, orient=orient)
+            t = dx * out_scale.view(1, C, 1, 1) if out_scale is not None else dx
+            return dx, (depth_to_space(t) if squeeze else t.contiguous())
+        _native.check(status)
+    return dx, dz

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_version_and_status_strings(lib):
-    assert lib.ifk_version() == 300
+    assert lib.ifk_version() == 400
     assert lib.ifk_status_string(0) == b"ok"
     for code in (-1, -2, -3, -4, -5, -6):
         assert lib.ifk_status_string(code) not in (b"ok", b"unknown ifk status")

@@ -832,3 +832,83 @@ def test_host_to_host_step_matches_the_resident_step():
     for k in range(2):
         assert torch.equal(hb["y"][k], ref_y[k].cpu()) and torch.equal(hb["dx"][k], ref_dx[k].cpu())
     assert torch.equal(hb["dw"], ref_dw.cpu())
+
+
+# ---- fused neighbours: ActNorm affine + Squeeze re-indexing inside the solve --------------
+FUSED_CASES = [
+    # (B, C, H, W, k, groups, squeeze, orient)       C, H, W: the SQUEEZED geometry the layer works on
+    (100, 12, 16, 16, 3, 1, True, "TL"), (100, 12, 16, 16, 3, 1, False, "TL"), (9, 24, 8, 8, 3, 1, True, "TL"),
+    (7, 48, 4, 4, 3, 1, True, "TL"), (5, 12, 16, 16, 3, 1, True, "BR"), (5, 12, 6, 10, 3, 1, False, "TR"),
+    (6, 48, 4, 4, 3, 4, True, "TL"), (300, 12, 6, 6, 3, 1, True, "BL"),
+    (4, 4, 14, 14, 2, 1, True, "TL"),        # shuffle-kernel geometry: served by the unfused sequence
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_fused_actnorm_squeeze_matches_oracle_composition(IF, case):
+    """y = L^-1(s * S(x) + b) and dz = S^T(s * L^-T g) in one launch each against the float64 oracle applied to the
+    explicitly squeezed / scaled tensors (reference actnorm.py:36, squeeze.py:5-24), plus the raw dX the dW kernel reads"""
+    B, C, H, W, k, groups, squeeze, orient = case
+    rng = np.random.default_rng(41)
+    xin = rng.standard_normal((B, C // 4, 2 * H, 2 * W) if squeeze else (B, C, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    s = np.exp(-0.3 * rng.standard_normal(C)).astype(np.float32)
+    b = (0.5 * rng.standard_normal(C)).astype(np.float32)
+    w = make_weight(rng, C, C, k, k, 0.02)
+
+    def sq(a):
+        Bn, Cn, Hn, Wn = a.shape
+        return a.reshape(Bn, Cn, Hn // 2, 2, Wn // 2, 2).transpose(0, 1, 3, 5, 2, 4).reshape(Bn, Cn * 4, Hn // 2, Wn // 2)
+
+    def unsq(a):
+        Bn, Cn, Hn, Wn = a.shape
+        return a.reshape(Bn, Cn // 4, 2, 2, Hn, Wn).transpose(0, 1, 4, 2, 5, 3).reshape(Bn, Cn // 4, Hn * 2, Wn * 2)
+
+    u = (sq(xin) if squeeze else xin).astype(np.float64) * s.astype(np.float64)[None, :, None, None] + \
+        b.astype(np.float64)[None, :, None, None]
+    y_ref = oracle.inverse(u, w.astype(np.float64), groups, threads=4, orient=orient)
+    dx_ref, _ = oracle.backward(g.astype(np.float64), y_ref, w.astype(np.float64), groups, threads=4, orient=orient)
+    t = dx_ref * s.astype(np.float64)[None, :, None, None]
+    dz_ref = unsq(t) if squeeze else t
+    wd = dev(w)
+    y = IF.inverse_fused(dev(xin), wd, in_scale=dev(s), in_bias=dev(b), squeeze=squeeze, groups=groups, orient=orient)
+    dx, dz = IF.bwd_input_fused(dev(g), wd, out_scale=dev(s), squeeze=squeeze, groups=groups, orient=orient)
+    torch.cuda.synchronize()
+    assert oracle.max_rel_err(y.cpu().numpy(), y_ref) < TOL
+    assert oracle.max_rel_err(dx.cpu().numpy(), dx_ref) < TOL
+    assert oracle.max_rel_err(dz.cpu().numpy(), dz_ref) < TOL
+    assert tuple(dz.shape) == xin.shape
+
+
+def test_fused_layer_matches_the_unfused_layers_through_autograd():
+    """ActNormInvFlow (one fused launch per direction) against ActNorm ops + Squeeze + inv_flow_with_pad composed in
+    PyTorch around the unfused kernels: outputs, log-det and the gradients of x, translation, log_scale and the weight"""
+    from inverse_flow_b200.layers import ActNormInvFlow, inv_conv_4d
+    from inverse_flow_b200 import functional as F2
+    torch.manual_seed(3)
+    for squeeze in (True, False):
+        layer = ActNormInvFlow(12, (3, 3), order="TL", squeeze=squeeze, groups=1).cuda()
+        x = torch.randn(20, 3, 32, 32, device="cuda") if squeeze else torch.randn(20, 12, 16, 16, device="cuda")
+        x = (x * 1.7 + 0.3).requires_grad_(True)
+        out, ldj = layer(x)
+        gsum = torch.randn_like(out)
+        (out * gsum).sum().backward()
+        got = [out.detach(), x.grad.clone(), layer.translation.grad.clone(), layer.log_scale.grad.clone(),
+               layer.conv.weight_fwd.grad.clone()]
+        # unfused reference composition with the same (now initialised) parameters
+        x2 = x.detach().clone().requires_grad_(True)
+        t2 = layer.translation.detach().clone().requires_grad_(True)
+        ls2 = layer.log_scale.detach().clone().requires_grad_(True)
+        w2 = layer.conv.weight_fwd.detach().clone().requires_grad_(True)
+        u = F2.space_to_depth(x2) if squeeze else x2
+        u = (u - t2.view(1, -1, 1, 1)) * torch.exp(-ls2).view(1, -1, 1, 1)
+        out2 = inv_conv_4d(u.contiguous(), w2, 1, "TL")
+        (out2 * gsum).sum().backward()
+        want = [out2.detach(), x2.grad, t2.grad, ls2.grad, w2.grad]
+        for a, b_, name in zip(got, want, ("out", "dx", "dtranslation", "dlog_scale", "dW")):
+            err = float((a - b_).abs().max() / b_.abs().max())
+            assert err < 2e-5, (squeeze, name, err)
+        assert torch.allclose(ldj, -layer.log_scale.sum().expand(20) * 16 * 16)
+        # reverse undoes forward
+        back = layer.reverse(out.detach())
+        assert float((back - x.detach()).abs().max() / x.detach().abs().max()) < 1e-4

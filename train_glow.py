@@ -8,9 +8,10 @@ One process per GPU; the batch is sharded over the ranks (weak scaling: the per-
 model's batch size) and the only communication is DistributedDataParallel's NCCL all-reduce of the
 gradient buckets -- replacing the reference's single-process nn.DataParallel
 (inf/if_multiGPU_imagenet32.py:410-411).  A step = forward (inverse-conv layers through the
-sm_100a kernels), loss, backward, gradient clipping, Adam update, as in the reference loop
-(inf/train/experiment.py:272-311) minus its per-layer print and parameter clamping.  Prints one
-JSON line (rank 0): images/s of the whole job, max over ranks.
+sm_100a kernels), loss with NaN samples zeroed (inf/train/experiment.py:191-192), backward, gradient clipping,
+Adam update under the linear learning-rate warm-up (experiment.py:197-202), as in the reference loop
+(experiment.py:272-311) minus its per-layer print and parameter clamping.  Prints one JSON line (rank 0):
+images/s of the whole job, max over ranks.
 """
 import argparse
 import json
@@ -32,6 +33,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--coupling-width", type=int, default=128)
     ap.add_argument("--groups", type=int, default=1)
+    ap.add_argument("--lr", type=float, default=1e-4)
+    ap.add_argument("--lr-warmup-steps", type=int, default=200,
+                    help="linear warm-up of the learning rate over this many optimizer steps (experiment.py:197-202)")
+    ap.add_argument("--init", default="reference", choices=["reference", "damped"],
+                    help="inverse-conv weights: the reference initialisation (dirac at the kernel's spatial centre + noise: "
+                         "for k = 3 that is the (1,1) tap, an operator whose inverse amplifies along the diagonal) or the "
+                         "same with the non-centre taps scaled by 0.05 (a well-conditioned start)")
     ap.add_argument("--no-graph", action="store_true",
                     help="run the step eagerly (default: the whole step -- forward, backward, clip, Adam -- is\n"
                          "captured in ONE CUDA graph on a single GPU; under DDP the step stays eager)")
@@ -44,22 +52,28 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to ONE JSON line: NCCL prints its version banner to stdout at any debug level
-        if "IFK_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["IFK_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # stdout stays ONE JSON line: NCCL's log (whatever NCCL_DEBUG the caller set) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     torch.manual_seed(0)                       # same initial weights on every rank
     model, shape, batch = glow.build(args.model, args.coupling_width, args.groups or None)
+    if args.init == "damped":
+        with torch.no_grad():
+            for inv in model.inv_layers:
+                centre = inv.weight_fwd[:, :, -1, -1].clone()
+                inv.weight_fwd.mul_(0.05)
+                inv.weight_fwd[:, :, -1, -1] = centre
     model = model.to(device)
     init_gen = torch.Generator(device=device).manual_seed(99)                 # same batch on every rank
     model.initialize(torch.rand((batch, *shape), generator=init_gen, device=device) - 0.5)
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
     use_graph = (world == 1) and not args.no_graph
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=use_graph)
+    # the learning rate lives in a device tensor so that the warm-up also works inside a captured graph
+    lr = torch.tensor(args.lr / max(args.lr_warmup_steps, 1), device=device)
+    opt = torch.optim.Adam(model.parameters(), lr=lr, capturable=True)
+    lr_step = torch.tensor(args.lr / max(args.lr_warmup_steps, 1), device=device)
+    lr_max = torch.tensor(args.lr, device=device)
     gen = torch.Generator(device=device).manual_seed(1234 + rank)
 
     def batch_of_images():
@@ -70,10 +84,13 @@ def main():
     def train_step(x):
         opt.zero_grad(set_to_none=False)
         latents, logp = net(x)
-        loss = -logp.mean() / (0.6931471805599453 * x[0].numel())
+        nll = -logp
+        nll = torch.where(nll != nll, torch.zeros_like(nll), nll)       # NaN samples count as 0 (experiment.py:191)
+        loss = nll.sum() / len(x) / (0.6931471805599453 * x[0].numel())
         loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
+        torch.minimum(lr + lr_step, lr_max, out=lr)                      # linear warm-up (experiment.py:197-202)
         return loss
 
     if use_graph:
@@ -122,7 +139,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
             "config": {"model": args.model, "input": list(shape), "batch_per_gpu": batch, "inv_conv_layers": n_inv,
-                       "coupling_width": args.coupling_width, "groups": args.groups,
+                       "coupling_width": args.coupling_width, "groups": args.groups, "init": args.init,
+                       "lr": args.lr, "lr_warmup_steps": args.lr_warmup_steps,
                        "parameters": sum(p.numel() for p in model.parameters()),
                        "parallelism": "DistributedDataParallel over NCCL, one process per GPU" if world > 1 else "single GPU",
                        "cuda_graph": bool(use_graph),
