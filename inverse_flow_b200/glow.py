@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .layers import inv_flow_no_pad
+from .layers import ActNormInvFlow, inv_flow_no_pad
 
 
 class Squeeze(nn.Module):
@@ -98,17 +98,25 @@ class IFGlow(nn.Module):
     out under a standard normal (split prior).  forward(x) -> (list of latents, log p(x))."""
 
     def __init__(self, shape=(1, 28, 28), num_blocks=2, block_size=16, kernel_size=2,
-                 coupling_width=128, groups=None, actnorm=True):
+                 coupling_width=128, groups=None, actnorm=True, fused=False):
         super().__init__()
         C, H, W = shape
         self.shape = tuple(shape)
         self.blocks = nn.ModuleList()
         self.inv_layers = []
+        self.fused = bool(fused and actnorm)     # ActNorm (and the block's Squeeze) inside the inverse-conv kernels
         for level in range(num_blocks):
             C, H, W = C * 4, H // 2, W // 2
             steps = nn.ModuleList()
-            for _ in range(block_size):
+            for k_step in range(block_size):
                 step = nn.ModuleList()
+                if self.fused:
+                    layer = ActNormInvFlow(C, (kernel_size, kernel_size), order="TL", squeeze=(k_step == 0), groups=groups)
+                    self.inv_layers.append(layer.conv)
+                    step.append(layer)
+                    step.append(Coupling(C, coupling_width))
+                    steps.append(step)
+                    continue
                 if actnorm:
                     step.append(ActNorm(C))
                 inv = inv_flow_no_pad(C, C, (kernel_size, kernel_size), groups=groups)
@@ -125,7 +133,8 @@ class IFGlow(nn.Module):
         logdet = torch.zeros(x.shape[0], device=x.device)
         latents = []
         for level, steps in enumerate(self.blocks):
-            x, _ = Squeeze()(x)
+            if not self.fused:                   # (fused: the first step of the block reads the un-squeezed tensor)
+                x, _ = Squeeze()(x)
             for step in steps:
                 for layer in step:
                     x, ld = layer(x)
@@ -147,7 +156,8 @@ class IFGlow(nn.Module):
             for step in reversed(self.blocks[level]):
                 for layer in reversed(step):
                     x = layer.reverse(x)
-            x = Squeeze().reverse(x)
+            if not self.fused:
+                x = Squeeze().reverse(x)
         return x
 
     @torch.no_grad()
@@ -173,6 +183,6 @@ CONFIGS = {
 }
 
 
-def build(name, coupling_width=128, groups=None):
+def build(name, coupling_width=128, groups=None, fused=False):
     shape, L, K, k, batch = CONFIGS[name]
-    return IFGlow(shape, L, K, k, coupling_width, groups), shape, batch
+    return IFGlow(shape, L, K, k, coupling_width, groups, fused=fused), shape, batch

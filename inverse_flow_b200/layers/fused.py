@@ -56,6 +56,7 @@ class ActNormInvFlow(FlowLayer):
         self.translation = nn.Parameter(torch.zeros(n_dims))
         self.log_scale = nn.Parameter(torch.zeros(n_dims))
         self.register_buffer("initialized", torch.tensor(0))
+        self._init_checked = False      # host-side memo of `initialized`: no device read per call (graph capture)
         self.conv = inv_flow_with_pad(n_dims, n_dims, kernel_size, order=order, groups=groups)
 
     def _initialize(self, input):
@@ -67,8 +68,10 @@ class ActNormInvFlow(FlowLayer):
             self.initialized.fill_(1)
 
     def forward(self, input, context=None, compute_expensive=False):
-        if not self.initialized:
-            self._initialize(input)
+        if not self._init_checked:
+            if not bool(self.initialized):
+                self._initialize(input)
+            self._init_checked = True
         out = actnorm_inv_conv_.apply(input, self.translation, self.log_scale, self.conv.weight_fwd, self.conv.groups,
                                       self.conv.order, self.squeeze)
         H, W = out.shape[2:]
@@ -76,7 +79,7 @@ class ActNormInvFlow(FlowLayer):
         return out, ldj
 
     def reverse(self, input, context=None, compute_expensive=False):
-        assert self.initialized
+        assert self._init_checked or bool(self.initialized)
         u = self.conv.reverse(input)
         u = u * torch.exp(self.log_scale).view(1, -1, 1, 1) + self.translation.view(1, -1, 1, 1)
         return IF.depth_to_space(u) if self.squeeze else u

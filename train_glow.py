@@ -40,6 +40,9 @@ def main():
                     help="inverse-conv weights: the reference initialisation (dirac at the kernel's spatial centre + noise: "
                          "for k = 3 that is the (1,1) tap, an operator whose inverse amplifies along the diagonal) or the "
                          "same with the non-centre taps scaled by 0.05 (a well-conditioned start)")
+    ap.add_argument("--fused", action="store_true",
+                    help="ActNorm (and each block's Squeeze) inside the inverse-conv kernels (layers.ActNormInvFlow)")
+    ap.add_argument("--ddp", action="store_true", help="N > 1: torch DistributedDataParallel (eager) instead of the flat-bucket all-reduce")
     ap.add_argument("--no-graph", action="store_true",
                     help="run the step eagerly (default: the whole step -- forward, backward, clip, Adam -- is\n"
                          "captured in ONE CUDA graph on a single GPU; under DDP the step stays eager)")
@@ -57,7 +60,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     torch.manual_seed(0)                       # same initial weights on every rank
-    model, shape, batch = glow.build(args.model, args.coupling_width, args.groups or None)
+    model, shape, batch = glow.build(args.model, args.coupling_width, args.groups or None, fused=args.fused)
     if args.init == "damped":
         with torch.no_grad():
             for inv in model.inv_layers:
@@ -67,8 +70,18 @@ def main():
     model = model.to(device)
     init_gen = torch.Generator(device=device).manual_seed(99)                 # same batch on every rank
     model.initialize(torch.rand((batch, *shape), generator=init_gen, device=device) - 0.5)
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-    use_graph = (world == 1) and not args.no_graph
+    # Data parallelism without a wrapper: every parameter's .grad is a view into ONE flat bucket, summed over the
+    # ranks by a single NCCL all-reduce per step -- which, unlike DistributedDataParallel's hooks, is captured in the
+    # step's CUDA graph together with everything else (--ddp keeps the PyTorch wrapper, eager)
+    use_ddp = world > 1 and args.ddp
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if use_ddp else model
+    use_graph = not use_ddp and not args.no_graph
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat_grad = torch.zeros(sum(p.numel() for p in params), device=device)
+    off = 0
+    for p in params:
+        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        off += p.numel()
     # the learning rate lives in a device tensor so that the warm-up also works inside a captured graph
     lr = torch.tensor(args.lr / max(args.lr_warmup_steps, 1), device=device)
     opt = torch.optim.Adam(model.parameters(), lr=lr, capturable=True)
@@ -88,6 +101,9 @@ def main():
         nll = torch.where(nll != nll, torch.zeros_like(nll), nll)       # NaN samples count as 0 (experiment.py:191)
         loss = nll.sum() / len(x) / (0.6931471805599453 * x[0].numel())
         loss.backward()
+        if world > 1 and not use_ddp:
+            dist.all_reduce(flat_grad)                                    # the one collective of the step (NCCL)
+            flat_grad.mul_(1.0 / world)
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         torch.minimum(lr + lr_step, lr_max, out=lr)                      # linear warm-up (experiment.py:197-202)
@@ -98,7 +114,7 @@ def main():
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(3):                      # warm-up outside capture (allocator, cuDNN, our modules)
+            for _ in range(3):                      # warm-up outside capture (allocator, cuDNN, NCCL, our modules)
                 train_step(static_x)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -139,17 +155,25 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
             "config": {"model": args.model, "input": list(shape), "batch_per_gpu": batch, "inv_conv_layers": n_inv,
-                       "coupling_width": args.coupling_width, "groups": args.groups, "init": args.init,
+                       "coupling_width": args.coupling_width, "groups": args.groups, "init": args.init, "fused_actnorm_squeeze": bool(args.fused),
                        "lr": args.lr, "lr_warmup_steps": args.lr_warmup_steps,
                        "parameters": sum(p.numel() for p in model.parameters()),
-                       "parallelism": "DistributedDataParallel over NCCL, one process per GPU" if world > 1 else "single GPU",
+                       "parallelism": ("DistributedDataParallel over NCCL, one process per GPU" if use_ddp else
+                                       "one process per GPU, one NCCL all-reduce of the flat gradient bucket per step "
+                                       "(inside the step's CUDA graph)") if world > 1 else "single GPU",
                        "cuda_graph": bool(use_graph),
                        "note": "PyTorch layers around the inverse-conv kernels are minimal stand-ins (out of scope): a "
                                "drop-in / scaling check, not a tuned number"},
             "loss_bits_per_dim_first_last": [losses[0], losses[-1]],
         }))
     if world > 1:
-        dist.destroy_process_group()
+        # a captured NCCL all-reduce keeps the communicator busy at tear-down (destroy_process_group then waits
+        # for ever): synchronise, meet at a barrier, and leave without the destructor
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
