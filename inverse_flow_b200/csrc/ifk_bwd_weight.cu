@@ -313,12 +313,19 @@ static QuadPlan make_quad_plan(const Geometry &g)
             const int waste = nz * nw * q.tpw - q.tiles;
             if (waste < best_waste) { best_waste = waste; q.nwarps = nw; q.nz = nz; }
         }
+        if (env().dw_cfg[0] > 0 && env().dw_cfg[0] <= kQuadMaxWarps) {       // tuning: warps per CTA
+            q.nwarps = env().dw_cfg[0];
+            q.tpw = (q.tiles + q.nwarps - 1) / q.nwarps;
+            if (q.tpw > 4) q.tpw = 4;
+            q.nz = (q.tiles + q.nwarps * q.tpw - 1) / (q.nwarps * q.tpw);
+        }
     }
     // batch chunks: about a third of the SMs in total, but at least ~3 quads per lane and what fits in smem
     const int qpi = g.H * g.W / 4;
     q.XN = g.Cg * g.H * g.W;
     const size_t per_img = (size_t)2 * q.XN * sizeof(float);
-    int want = (kNumSM / 3 + g.groups * q.nz - 1) / (g.groups * q.nz);
+    const int ctas = env().dw_cfg[1] > 0 ? env().dw_cfg[1] : kNumSM / 3 + 1;       // 50: two images per CTA at a batch of 100
+    int want = (ctas + g.groups * q.nz - 1) / (g.groups * q.nz);
     if (want < 1) want = 1;
     int per_chunk = (g.B + want - 1) / want;
     while (per_chunk * qpi < 96 && per_chunk < g.B) per_chunk++;

@@ -22,6 +22,7 @@ struct EnvKnobs {
     int stream_cfg[2];   // IFK_STREAM_CFG="cc,nv"          (0 = unset)
     int window_cfg[4];   // IFK_WINDOW_CFG="cc,nv,cs,rp"    (0 = unset)
     int wave_cfg[4];     // IFK_WAVE_CFG="cc,ns,vec,threads" (0 = unset) : tuning
+    int dw_cfg[2];       // IFK_DW_CFG="warps,ctas"       (0 = unset) : tuning of the quad dW kernel
     int split_cfg[2];    // IFK_SPLIT_CFG="nsh"            (0 = unset) : tuning
     bool pins_other_solver() const { return solve_global || solve_stream || solve_window || has_solve_cfg; }
 };

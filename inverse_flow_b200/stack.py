@@ -103,18 +103,21 @@ class InvConvStack:
                                                     st.prepared_all.data_ptr(), st.pf, s))
 
     def prepare_all_forked(self):
-        """the prepares of every stage depend on the weights only: forked onto a side stream at the start of
-        the step, stage k's runs while the earlier stages' solves do; forward_stage joins it"""
+        """the prepares of every stage depend on the weights only and are latency-bound (one small CTA per layer and
+        tap): they run CONCURRENTLY, one stream per stage, and the first solve waits for all of them -- the critical
+        path is one prepare, and no prepare CTA competes with the latency-bound solve chain afterwards"""
         main = torch.cuda.current_stream(self.device)
         self._prep_events = {}
-        side = self.sides[-1]
-        side.wait_stream(main)
-        for st in self.stages[1:]:
+        for k, st in enumerate(self.stages[1:]):
+            side = self.sides[-1 - (k % len(self.sides))]
+            side.wait_stream(main)
             self.prepare_stage(st, side)
             ev = torch.cuda.Event()
             ev.record(side)
             self._prep_events[id(st)] = ev
-        self.prepare_stage(self.stages[0])      # (the waits in forward_stage join the side stream again)
+        self.prepare_stage(self.stages[0])
+        for st in self.stages[1:]:               # join now: the solves start only when every prepare has finished
+            main.wait_event(self._prep_events.pop(id(st)))
 
     def forward_stage(self, st, prepared=False):
         lib, s = self.lib, self._stream()
@@ -318,9 +321,10 @@ class InvConvStack:
                 ev = torch.cuda.Event()
                 ev.record(cp)
                 ev_g.append(ev)
+        self.prepare_all_forked()                  # weights only: runs while the first images are still in flight
         for k, st in enumerate(self.stages):
             main.wait_event(ev_x[k])
-            self.forward_stage(st)
+            self.forward_stage(st, prepared=True)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(cp):

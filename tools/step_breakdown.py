@@ -77,10 +77,21 @@ def main():
                                                                    ws.data_ptr(), stack._stream()))
         stack.finish_weight_gradients()
 
+    def fwd_solves_only():
+        for st in stack.stages:
+            stack.forward_stage(st, prepared=True)
+
+    def prepares_only():
+        for st in stack.stages:
+            stack.prepare_stage(st)
+
     stack.forward_backward()
     torch.cuda.synchronize()
     res = {"workload": args.workload, "layers": sum(st.n for st in stack.stages)}
     res["forward_ms"] = timed(graph_of(stack.forward), flush)
+    res["forward_main_stream_graph_ms"] = timed(graph_of(stack.forward, stack.main), flush)
+    res["forward_solves_only_ms"] = timed(graph_of(fwd_solves_only), flush)
+    res["prepares_only_ms"] = timed(graph_of(prepares_only), flush)
     res["backward_dx_chain_ms"] = timed(graph_of(bwd_dx_only), flush)
     res["dw_serial_one_stream_ms"] = timed(graph_of(dw_only), flush)
     res["backward_full_ms"] = timed(graph_of(stack.backward, stack.main), flush)
