@@ -62,7 +62,8 @@ WORKLOADS = {
 # capture of that kernel at the workload's stage-1 shape: workload -> (bytes, where it is recorded)
 PROFILED_DRAM_TRAFFIC = {
     "glow_mnist": (327168, "profiles/r01_ncu_shfl_100x4x14.txt (dram__bytes_read 327168 + dram__bytes_write 0)"),
-    "glow_imagenet32": (None, None),      # filled from profiles/r02_ncu_wave_100x12x16.txt when captured
+    "glow_imagenet32": (1262592, "profiles/r02_ncu_wave_100x12x16.txt (dram__bytes_read 1262592 + dram__bytes_write 0: the "
+                                 "output stays in L2 for the next layer)"),
 }
 
 def parallelism_text(n_gpus, comm_kind=None):
