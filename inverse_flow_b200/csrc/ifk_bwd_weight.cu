@@ -349,6 +349,13 @@ struct QuadParams {
     unsigned m_qpi, m_qpr;     // ceil(2^32 / qpi), ceil(2^32 / qpr)
 };
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 template <int KH, int KW, int TC, int TKC, bool FW>
 __global__ void __launch_bounds__(kQuadMaxWarps * 32)
 bwd_weight_quad_kernel(const QuadParams p)
@@ -391,46 +398,44 @@ bwd_weight_quad_kernel(const QuadParams p)
     }
 
     const bool fh = p.orient & 2;
-    const int rstep = fh ? W : -W;            // row of tap qh: h - qh (or h + qh on a reflected axis)
     const int nquads = n_img * p.qpi;
     float *out = p.partial + ((size_t)chunk * p.C + (size_t)G * Cg) * Cg * K;   // [c][kc][t]
+    // 32-bit shared-space addressing throughout the quad loop: generic 64-bit pointer arithmetic and pointer selects
+    // were as many instructions as the FMAs themselves (266 of 554 per quad; every one costs an issue slot)
+    const uint32_t buf_s = smem_u32(buf), zero_s = smem_u32(zero4);
+    const uint32_t HW4 = (uint32_t)HW * 4u, img_b = (uint32_t)(2 * XN) * 4u, y_b = (uint32_t)XN * 4u;
+    const uint32_t rstep4 = fh ? (uint32_t)W * 4u : (uint32_t)(-W * 4);       // row of tap qh: h - qh (h + qh reflected)
+    const uint32_t side4 = FW ? 16u : (uint32_t)-16;
 
     for (int tw = 0; tw < p.tpw; tw++) {
         const int tile = (blockIdx.z * (blockDim.x >> 5) + warp) * p.tpw + tw;
         if (tile >= p.tiles) break;                              // warp-uniform
         const int c0 = (tile / p.ntk) * TC, k0 = (tile % p.ntk) * TKC;
+        const uint32_t d_off = (uint32_t)(c0 * HW) * 4u, y_off = y_b + (uint32_t)(k0 * HW) * 4u;
         float acc[NACC];
 #pragma unroll
         for (int i = 0; i < NACC; i++) acc[i] = 0.f;
         for (int u = lane; u < nquads; u += 32) {
             const int img = p.m_qpi ? (int)__umulhi((unsigned)u, p.m_qpi) : u, r = u - img * p.qpi;     // magic 0: divisor 1
             const int h = p.m_qpr ? (int)__umulhi((unsigned)r, p.m_qpr) : r, wq = r - h * p.qpr;
-            const float *dimg = buf + (size_t)(2 * img) * XN, *yimg = dimg + XN;
-            const int pix = h * W + 4 * wq;
+            const uint32_t qbase = buf_s + (uint32_t)img * img_b + (uint32_t)(h * W + 4 * wq) * 4u;   // dX plane 0, the quad
             float4 d4[TC];
 #pragma unroll
-            for (int i = 0; i < TC; i++) d4[i] = *reinterpret_cast<const float4 *>(dimg + (c0 + i) * HW + pix);
+            for (int i = 0; i < TC; i++) d4[i] = lds_f4(qbase + d_off + (uint32_t)i * HW4);
             // window of 8 columns per (y channel, tap row): [4wq-4, 4wq+3], reflected: [4wq, 4wq+7]
             // neighbours outside the image read a zeroed 16-byte cell instead: no branch, no predicated load
             const bool side_ok = FW ? (wq + 1 < p.qpr) : (wq > 0);
-            const float *ybase = yimg + k0 * HW + pix;
-            const float *row_ptr[KH], *side_ptr[KH];
+            const uint32_t ybase = qbase + y_off;
 #pragma unroll
             for (int qh = 0; qh < KH; qh++) {
                 const int hh = fh ? h + qh : h - qh;
-                const bool row_ok = hh >= 0 && hh < p.H;
-                row_ptr[qh] = row_ok ? ybase + qh * rstep : zero4;
-                side_ptr[qh] = row_ok && side_ok ? ybase + qh * rstep + (FW ? 4 : -4) : zero4;
-            }
+                const bool row_ok = (unsigned)hh < (unsigned)p.H;
+                const uint32_t rowa = ybase + (uint32_t)qh * rstep4;
 #pragma unroll
-            for (int k = 0; k < TKC; k++) {
-#pragma unroll
-                for (int qh = 0; qh < KH; qh++) {
-                    // a4: the quad's own columns, b4: the four columns beside it (channel k0 + k: k planes further;
-                    // the zero cell is re-read for every k, its offset masked to 0)
-                    const bool rz = row_ptr[qh] == zero4, sz = side_ptr[qh] == zero4;
-                    const float4 a4 = *reinterpret_cast<const float4 *>(row_ptr[qh] + (rz ? 0 : k * HW));
-                    const float4 b4 = *reinterpret_cast<const float4 *>(side_ptr[qh] + (sz ? 0 : k * HW));
+                for (int k = 0; k < TKC; k++) {
+                    // a4: the quad's own columns, b4: the four columns beside it (channel k0 + k: k planes further)
+                    const float4 a4 = lds_f4(row_ok ? rowa + (uint32_t)k * HW4 : zero_s);
+                    const float4 b4 = lds_f4(row_ok && side_ok ? rowa + (uint32_t)k * HW4 + side4 : zero_s);
                     // win[j]: column 4wq - 4 + j (plain) / 4wq + j (reflected)
                     const float win[8] = {FW ? a4.x : b4.x, FW ? a4.y : b4.y, FW ? a4.z : b4.z, FW ? a4.w : b4.w,
                                           FW ? b4.x : a4.x, FW ? b4.y : a4.y, FW ? b4.z : a4.z, FW ? b4.w : a4.w};

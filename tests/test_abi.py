@@ -181,3 +181,46 @@ def test_kernel_selection_is_well_formed_over_the_sweep_grid(lib):
                         assert lib.ifk_bwd_weight_workspace_bytes(ctypes.byref(p)) > 0
     # the grid exercises every solve kernel
     assert set(kinds) == {"shfl", "wave", "smem", "window", "stream", "global"}, kinds
+
+
+def test_fused_entry_points_validate_before_any_launch(lib):
+    """ifk_inverse_fused_f32 / ifk_bwd_input_fused_f32 (include/ifk.h, struct ifk_fused): argument errors and the
+    'not served by the wavefront kernel' answer come back without touching a device"""
+    assert ctypes.sizeof(_native.Fused) == 3 * ctypes.sizeof(ctypes.c_void_p) + 2 * ctypes.sizeof(ctypes.c_int) or \
+        ctypes.sizeof(_native.Fused) == 4 * ctypes.sizeof(ctypes.c_void_p)            # 3 pointers + int (+ padding)
+    header = open(os.path.join(ROOT, "include", "ifk.h")).read()
+    struct = header[header.index("typedef struct ifk_fused"):header.index("} ifk_fused;")]
+    assert re.findall(r"(\w+)[;,]", struct.replace("*", "")) == ["in_scale", "in_bias", "out_scale", "squeeze"]
+    dummy = ctypes.c_void_p(16)
+    ok = _native.problem(2, 12, 16, 16, 3, 3, 12, 1)
+    f = _native.Fused(None, None, None, 1)
+    assert lib.ifk_inverse_fused_f32(ctypes.byref(ok), None, dummy, dummy, dummy, None) == -1          # no ifk_fused
+    assert lib.ifk_inverse_fused_f32(ctypes.byref(ok), ctypes.byref(f), None, dummy, dummy, None) == -1
+    assert lib.ifk_bwd_input_fused_f32(ctypes.byref(ok), ctypes.byref(f), dummy, dummy, dummy, None, None) == -1   # dz is required
+    bad = _native.Fused(None, None, None, 2)
+    assert lib.ifk_inverse_fused_f32(ctypes.byref(ok), ctypes.byref(bad), dummy, dummy, dummy, None) == -8
+    # squeeze needs (C / groups) % 4 == 0
+    g6 = _native.problem(2, 12, 16, 16, 3, 3, 12, 2)
+    assert lib.ifk_inverse_fused_f32(ctypes.byref(g6), ctypes.byref(f), dummy, dummy, dummy, None) == -2
+    # geometries without a pipelined wavefront variant: the caller runs the unfused sequence
+    mnist = _native.problem(2, 4, 14, 14, 2, 2, 4, 1)
+    assert lib.ifk_inverse_fused_f32(ctypes.byref(mnist), ctypes.byref(f), dummy, dummy, dummy, None) == _native.ERR_UNSUPPORTED
+    empty = _native.problem(0, 12, 16, 16, 3, 3, 12, 1)
+    assert lib.ifk_inverse_fused_f32(ctypes.byref(empty), ctypes.byref(f), None, dummy, None, None) == 0
+
+
+def test_split_kernel_is_opt_in_and_limited_to_the_rows_it_holds(lib, monkeypatch):
+    d = lambda *a: _native.describe_solve(_native.problem(*a))
+    assert d(100, 12, 16, 16, 3, 3, 12, 1).startswith("wave<")
+    monkeypatch.setenv("IFK_SOLVE_SPLIT", "1")
+    assert d(100, 12, 16, 16, 3, 3, 12, 1).startswith("split<") and "helper cc=6 ns=4" in d(100, 12, 16, 16, 3, 3, 12, 1)
+    assert d(100, 24, 8, 8, 3, 3, 24, 1).startswith("split<")
+    assert d(100, 12, 32, 32, 3, 3, 12, 1).startswith("wave<")          # 32 rows: more than the split kernel's 16 slots
+    assert d(100, 48, 4, 4, 3, 3, 48, 1).startswith("wave<")            # no split variant for Cg = 48
+    monkeypatch.setenv("IFK_SPLIT_CFG", "8")
+    assert "ns=8" in d(100, 12, 16, 16, 3, 3, 12, 1)
+    # the prepared buffer grows by the split kernel's packed copy
+    p = _native.problem(1, 12, 16, 16, 3, 3, 12, 1)
+    with_split = lib.ifk_prepared_floats(ctypes.byref(p))
+    monkeypatch.setenv("IFK_SOLVE_SPLIT", "0")
+    assert lib.ifk_prepared_floats(ctypes.byref(p)) < with_split

@@ -96,3 +96,18 @@ def test_fincflow_layer_surface():
                                                 "conv_tl.conv.weight", "conv_tr.conv.weight"]
     with pytest.raises(AssertionError):
         Finc_FlowUnit(6, 6, 3)
+
+
+def test_squeeze_helpers_match_the_reference_formulas():
+    """functional.space_to_depth / depth_to_space (the unfused path of the fused ActNorm/Squeeze layer and its tests)
+    restate reference inf/layers/squeeze.py:5-24: checked against an index-by-index definition on the CPU"""
+    import torch
+    from inverse_flow_b200 import functional as IF
+    x = torch.arange(2 * 3 * 4 * 6, dtype=torch.float32).view(2, 3, 4, 6)
+    y = IF.space_to_depth(x)
+    assert y.shape == (2, 12, 2, 3)
+    for c in range(3):
+        for i in range(2):
+            for j in range(2):
+                assert torch.equal(y[:, c * 4 + i * 2 + j], x[:, c, i::2, j::2])
+    assert torch.equal(IF.depth_to_space(y), x)

@@ -66,6 +66,46 @@ def main():
                                                           st.dxs[i].data_ptr(), stack._stream()))
                 g = st.dxs[i]
 
+    def bwd_dx_with_event_records():
+        """the dX chain with an (unused) event recorded after every solve: does a record between two kernels of the
+        capturing stream cost the programmatic dependent launch overlap?"""
+        import ctypes
+        from inverse_flow_b200 import _native
+        main = torch.cuda.current_stream()
+        for st in stack.stages:
+            ps = ctypes.byref(st.problem_stable)
+            g = st.grad_in
+            for i in reversed(range(st.n)):
+                _native.check(stack.lib.ifk_bwd_input_f32(ps, g.data_ptr(), st.prepared[i].data_ptr(),
+                                                          st.dxs[i].data_ptr(), stack._stream()))
+                ev = torch.cuda.Event()
+                ev.record(main)
+                g = st.dxs[i]
+
+    def bwd_dx_with_forked_noops():
+        """the dX chain with a fork after every solve whose side stream runs a trivial kernel"""
+        import ctypes
+        from inverse_flow_b200 import _native
+        main = torch.cuda.current_stream()
+        sides = stack.sides
+        k = 0
+        for st in stack.stages:
+            ps = ctypes.byref(st.problem_stable)
+            g = st.grad_in
+            for i in reversed(range(st.n)):
+                _native.check(stack.lib.ifk_bwd_input_f32(ps, g.data_ptr(), st.prepared[i].data_ptr(),
+                                                          st.dxs[i].data_ptr(), stack._stream()))
+                side = sides[k % len(sides)]
+                k += 1
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    tiny.add_(1.0)
+                g = st.dxs[i]
+        for side in sides:
+            main.wait_stream(side)
+
+    tiny = torch.zeros(32, device="cuda")
+
     def dw_only():
         import ctypes
         from inverse_flow_b200 import _native
@@ -93,6 +133,8 @@ def main():
     res["forward_solves_only_ms"] = timed(graph_of(fwd_solves_only), flush)
     res["prepares_only_ms"] = timed(graph_of(prepares_only), flush)
     res["backward_dx_chain_ms"] = timed(graph_of(bwd_dx_only), flush)
+    res["backward_dx_chain_event_records_ms"] = timed(graph_of(bwd_dx_with_event_records, stack.main), flush)
+    res["backward_dx_chain_forked_noops_ms"] = timed(graph_of(bwd_dx_with_forked_noops, stack.main), flush)
     res["dw_serial_one_stream_ms"] = timed(graph_of(dw_only), flush)
     res["backward_full_ms"] = timed(graph_of(stack.backward, stack.main), flush)
     res["step_ms"] = timed(graph_of(stack.forward_backward, stack.main), flush)
