@@ -545,8 +545,17 @@ bwd_weight_reduce_thread_kernel(const float *__restrict__ partial, float *__rest
         float s = 0.f;
         if (kc < Cg && !(qh == 0 && qw == 0 && kc >= cl)) {
             const float *src = partial + ((size_t)c * Cg + kc) * K + (qh * KW + qw);
-            for (int n = 0; n < nchunks; n++) s += __ldg(src + (size_t)n * chunk_stride);
-            s = -s;
+            // four independent partial sums in a FIXED association: deterministic, and the loads pipeline
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int n = 0;
+            for (; n + 3 < nchunks; n += 4) {
+                s0 += __ldg(src + (size_t)n * chunk_stride);
+                s1 += __ldg(src + (size_t)(n + 1) * chunk_stride);
+                s2 += __ldg(src + (size_t)(n + 2) * chunk_stride);
+                s3 += __ldg(src + (size_t)(n + 3) * chunk_stride);
+            }
+            for (; n < nchunks; n++) s0 += __ldg(src + (size_t)n * chunk_stride);
+            s = -((s0 + s1) + (s2 + s3));
         }
         dw[e] = s;
     }
@@ -602,7 +611,7 @@ int launch_bwd_weight_reduce(const Geometry &g, int count, const void *workspace
     const int total = g.C * g.Cw * g.K;
     const int nchunks = g.B > 0 ? stage1_chunks(g) : 0;
     const size_t pstride = workspace_stride / sizeof(float);
-    if (nchunks >= 16) {
+    if (nchunks >= 96) {                          // (a warp per element pays only for long chunk lists)
         int blocks = (total + 7) / 8;             // 8 warps per CTA, one element per warp
         const int cap = kNumSM * 8 / (count < 8 ? count : 8) + 1;
         if (blocks > cap) blocks = cap;

@@ -83,6 +83,7 @@ class InvConvStack:
         # (lowest priority: the dependent chain of solves on the capturing stream gets freed SMs first)
         self.sides = [torch.cuda.Stream(device=self.device, priority=0)
                       for _ in range(int(os.environ.get("IFK_STACK_SIDE_STREAMS", "8")))]
+        self.reduce_stream = torch.cuda.Stream(device=self.device, priority=0)
         self.main = torch.cuda.Stream(device=self.device, priority=-1)      # the stream graphs are captured on
         self._side_rr = 0
         self._sides_forked = []           # side streams forked since the last join (a graph capture must
@@ -173,10 +174,24 @@ class InvConvStack:
         for st in self.stages:
             self.forward_stage(st, prepared=True)
 
+    def finish_stage_async(self, st, local=False):
+        """stage 2 of dW for ONE stage on the reduce stream, behind the stage's dW kernels: it overlaps the next
+        stage's dX chain instead of waiting at the end of the backward pass"""
+        red = self.reduce_stream
+        for side in self._sides_forked:
+            red.wait_stream(side)
+        _native.check(self.lib.ifk_bwd_weight_reduce_many_f32(
+            ctypes.byref(st.problem), st.n, st.workspace.data_ptr(), st.ws_floats * 4,
+            (st.dw_local_base if local else st.dw_base).data_ptr(), st.w_stride, ctypes.c_void_p(red.cuda_stream)))
+
     def backward(self):
+        main = torch.cuda.current_stream(self.device)
+        self.reduce_stream.wait_stream(main)          # fork (a capture must see the stream join and leave)
         for st in self.stages:
             self.backward_stage(st)
-        self.finish_weight_gradients()
+            self.finish_stage_async(st)
+        main.wait_stream(self.reduce_stream)          # join: transitively every dW side stream
+        self._sides_forked = []
 
     def forward_backward(self):
         self.forward()
@@ -253,22 +268,27 @@ class InvConvStack:
 
             def run():
                 main = torch.cuda.current_stream(self.device)
+                red = self.reduce_stream
                 self.forward()
+                red.wait_stream(main)                            # fork the reduce stream
                 for st in last:
                     self.backward_stage(st)
-                self.finish_weight_gradients(last, local=True)
+                    self.finish_stage_async(st, local=True)      # stage 2 behind the stage's dW kernels, off the main stream
                 side = self.sides[-1]
                 if rest:
-                    side.wait_stream(main)                       # fork: the last stage's slice travels now
+                    side.wait_stream(red)                        # fork: the last stage's slice travels now
                     with torch.cuda.stream(side):
                         comm.allreduce(self.grad_bucket, offset=split, numel=n_all - split)
                     for st in rest:
                         self.backward_stage(st)
-                    self.finish_weight_gradients(rest, local=True)
+                        self.finish_stage_async(st, local=True)
+                    main.wait_stream(red)
                     comm.allreduce(self.grad_bucket, offset=0, numel=split)
                     main.wait_stream(side)                       # join
                 else:
+                    main.wait_stream(red)
                     comm.allreduce(self.grad_bucket)
+                self._sides_forked = []
 
             warm = torch.cuda.Stream()
             warm.wait_stream(torch.cuda.current_stream())
