@@ -482,7 +482,10 @@ def run_ours(args):
     bytes_io = [0, 0]
 
     def one_step_host():
-        if world > 1:
+        if world > 1 and args.comm == "peer":
+            # the host-to-host pipeline with the fused peer all-reduce inside: ONE graph per step, copies overlapped
+            bytes_io[0], bytes_io[1] = stack.step_host(hb, parallel=True)
+        elif world > 1:
             h2d = d2h = 0
             for st, x, g in zip(stack.stages, hb["x"], hb["g"]):
                 st.act[0].copy_(x, non_blocking=True)

@@ -323,7 +323,7 @@ class InvConvStack:
         hb["dw"] = torch.empty(self.grad_bucket.shape, **pin)
         return hb
 
-    def _host_pipeline(self, hb):
+    def _host_pipeline(self, hb, parallel=False):
         """x, g from pinned host memory -> forward + backward -> y, dX, dW to pinned host memory, with
         the copies on their own stream: stage k+1's upload and stage k's download overlap compute."""
         main = torch.cuda.current_stream(self.device)
@@ -358,30 +358,35 @@ class InvConvStack:
             with torch.cuda.stream(cp):
                 cp.wait_event(done)
                 hb["dx"][k].copy_(st.dx, non_blocking=True)
-        self.finish_weight_gradients()
+        if parallel:                                                 # data-parallel: this rank's dW into the peer-mapped
+            self.finish_weight_gradients(local=True)                 # bucket, then the fused all-reduce over the ranks
+            self.comm.allreduce(self.grad_bucket)
+        else:
+            self.finish_weight_gradients()
         hb["dw"].copy_(self.grad_bucket, non_blocking=True)
         main.wait_stream(cp)                                         # join
 
-    def capture_host(self, hb):
-        """the whole host-to-host step as ONE CUDA graph (memcpy nodes included)."""
+    def capture_host(self, hb, parallel=False):
+        """the whole host-to-host step as ONE CUDA graph (memcpy nodes included; `parallel`: with the gradient
+        exchange over the ranks -- every rank must capture and replay it the same number of times)."""
         with torch.cuda.device(self.device):
             self.copy = torch.cuda.Stream(device=self.device)
             warm = torch.cuda.Stream()
             warm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(warm):
-                self._host_pipeline(hb)
+                self._host_pipeline(hb, parallel)
             torch.cuda.current_stream().wait_stream(warm)
             torch.cuda.synchronize()
             self.graph_host = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_host, stream=self.main):
-                self._host_pipeline(hb)
+                self._host_pipeline(hb, parallel)
         self._host_buffers = hb
         return self
 
-    def step_host(self, hb):
+    def step_host(self, hb, parallel=False):
         """host x, g -> device -> forward+backward -> host y, dX, dW.  Returns (h2d, d2h) bytes."""
         if getattr(self, "graph_host", None) is None or self._host_buffers is not hb:
-            self.capture_host(hb)
+            self.capture_host(hb, parallel)
         self.graph_host.replay()
         torch.cuda.current_stream(self.device).synchronize()
         n_act = sum(x.numel() for x in hb["x"])
