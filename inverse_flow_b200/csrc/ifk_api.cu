@@ -25,7 +25,7 @@ int make_geometry(const ifk_problem *p, Geometry *g)
         return IFK_ERR_UNSUPPORTED;
     g->KD = (int)kd;
     g->KDP = round_up(g->KD, 4);
-    if ((size_t)3 * g->Cg * (g->Cg + 1) * sizeof(float) > (size_t)kMaxSmemBytes)
+    if (prepare_smem_bytes(g->Cg) > (size_t)kMaxSmemBytes)
         return IFK_ERR_UNSUPPORTED;                      // ifk_prepare stages three Cg x Cg matrices
     return IFK_OK;
 }

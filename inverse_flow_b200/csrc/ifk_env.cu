@@ -49,6 +49,7 @@ static void parse_env()
         sscanf(e, "%d,%d,%d,%d", &k.wave_cfg[0], &k.wave_cfg[1], &k.wave_cfg[2], &k.wave_cfg[3]);
     if (const char *e = getenv("IFK_DW_CFG")) sscanf(e, "%d,%d", &k.dw_cfg[0], &k.dw_cfg[1]);
     if (const char *e = getenv("IFK_SPLIT_CFG")) sscanf(e, "%d,%d", &k.split_cfg[0], &k.split_cfg[1]);
+    if (const char *e = getenv("IFK_PREP_CFG")) sscanf(e, "%d,%d", &k.prep_cfg[0], &k.prep_cfg[1]);
     std::lock_guard<std::mutex> lock(g_env_mutex);
     g_env = k;
     g_env_generation++;

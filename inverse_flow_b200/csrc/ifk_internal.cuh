@@ -29,6 +29,7 @@ inline const float *prepared_dir(const Geometry &g, const float *prepared, int d
 }
 
 // launchers (each returns 0 or a cudaError_t)
+size_t prepare_smem_bytes(int Cg);      // dynamic shared memory of prepare_kernel (ifk_prepare.cu)
 int launch_prepare(const Geometry &g, const float *weight, float *prepared, cudaStream_t s, int count = 1,
                    size_t weight_stride = 0, size_t prepared_stride = 0);
 int launch_solve(const Geometry &g, const float *in, const float *prepared, float *out,

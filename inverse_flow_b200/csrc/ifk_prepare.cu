@@ -15,22 +15,45 @@
 // be prepared by a single launch.  Every CTA rebuilds T in shared memory (forward
 // substitution, one thread per column, 4 independent partial sums: ~Cg^2/2 cycles) and then
 // forms its slab of taps as small dense products out of shared memory.
+//
+// The products are what the launch costs at wide groups (Cg = 48: 864 CTAs x Cg^3 multiply-adds, each
+// fed by two shared-memory loads -- the whole chip's LDS bandwidth for ~100 us, ahead of the first
+// solve of the step).  They are register-tiled: a thread forms four adjacent input columns of one
+// output row, per k one broadcast load of T and one 128-bit load of the staged tap (which is stored
+// transposed for the adjoint, so that both directions read rows): 3 instead of 8 shared-memory
+// wavefronts per 128 multiply-adds.  IFK_PREP_CFG="legacy,taps_per_cta" pins the round-1 loop / the slab size.
+#include "ifk_env.cuh"
 #include "ifk_internal.cuh"
 
 namespace ifk {
 
 constexpr int kPrepThreads = 256;
 
+// row stride of the staged tap of the tiled product: rows 16-byte aligned, and an odd multiple of 4 so that the
+// transposing stores of the adjoint spread over 8 banks
+__host__ __device__ inline int prepare_tap_stride(int Cg)
+{
+    int rs = (Cg + 3) / 4 * 4;
+    return rs % 8 == 0 ? rs + 4 : rs;
+}
+size_t prepare_smem_bytes(int Cg)
+{
+    const int ts = Cg + 1, rs = prepare_tap_stride(Cg);
+    return ((size_t)2 * Cg * ts + (size_t)Cg * (rs > ts ? rs : ts)) * sizeof(float);
+}
+
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_kernel(const float *__restrict__ weight, float *__restrict__ prepared, int C, int Cg, int Cw,
                int KH, int KW, int KD, int KDP, int taps_per_cta, int groups, size_t weight_stride,
-               size_t prepared_stride)
+               size_t prepared_stride, int tiled)
 {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int TS = Cg + 1;                 // padded row stride: column walks hit distinct banks
+    const int RS = prepare_tap_stride(Cg);
     float *A = sm;                         // [Cg][TS] strictly-lower centre tap A0
     float *T = A + Cg * TS;                // [Cg][TS] T0 = (I + A0)^-1 (unit lower triangular)
-    float *Wq = T + Cg * TS;               // [Cg][TS] one tap, rows = weight output channel
+    float *Wq = T + Cg * TS;               // one tap: legacy [Cg][TS], rows = weight output channel; tiled [k][RS], see below
+                                           // (2 Cg (Cg+1) floats in front of it: a multiple of 16 bytes)
     const int G = blockIdx.x % groups, layer = blockIdx.x / groups, dir = blockIdx.y;
     weight += (size_t)layer * weight_stride;       // batched: one weight tensor per layer
     prepared += (size_t)layer * prepared_stride;
@@ -45,6 +68,11 @@ prepare_kernel(const float *__restrict__ weight, float *__restrict__ prepared, i
         const int i = e / Cg, k = e - i * Cg;
         A[i * TS + k] = k < i ? __ldg(wg + i * row_stride + k * tap_stride + centre) : 0.f;
     }
+    if (tiled)                              // pad columns of the staged tap: read by the last tile, never written again
+        for (int e = tid; e < Cg * (RS - Cg); e += kPrepThreads) {
+            const int k = e / (RS - Cg);
+            Wq[k * RS + Cg + (e - k * (RS - Cg))] = 0.f;
+        }
     __syncthreads();
     // column j of T0 by forward substitution: T[i][j] = [i==j] - sum_{j<=k<i} A[i][k] T[k][j]
     for (int j = tid; j < Cg; j += kPrepThreads) {
@@ -84,6 +112,39 @@ prepare_kernel(const float *__restrict__ weight, float *__restrict__ prepared, i
         const int qh = t / KW, qw = t - qh * KW;
         const int a = (KH - 1 - qh) * KW + (KW - 1 - qw);
         __syncthreads();                       // previous tap's readers are done with Wq
+        if (tiled) {
+            // out[co][ci] = -sum_k L[co][k] R[k][ci] with R[k][ci] = W[k][ci], k <= co (forward: L = T) or
+            // R[k][ci] = W[ci][k], k >= co (adjoint: L = T^T, read in place with stride TS)
+            for (int e = tid; e < Cg * Cg; e += kPrepThreads) {
+                const int r = e / Cg, c = e - r * Cg;
+                const float w = __ldg(wg + r * row_stride + c * tap_stride + a);
+                Wq[dir == 0 ? r * RS + c : c * RS + r] = w;
+            }
+            __syncthreads();
+            const int Cg4 = (Cg + 3) >> 2;
+            for (int e = tid; e < Cg * Cg4; e += kPrepThreads) {
+                const int co = e / Cg4, j4 = (e - co * Cg4) * 4;
+                const int k0 = dir == 0 ? 0 : co, k1 = dir == 0 ? co + 1 : Cg;
+                const float *lp = dir == 0 ? T + co * TS : T + co;
+                const int ls = dir == 0 ? 1 : TS;
+                const float *rp = Wq + j4;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int k = k0; k < k1; k++) {
+                    const float l = lp[k * ls];
+                    const float4 r4 = *reinterpret_cast<const float4 *>(rp + k * RS);
+                    a0 = fmaf(l, r4.x, a0);
+                    a1 = fmaf(l, r4.y, a1);
+                    a2 = fmaf(l, r4.z, a2);
+                    a3 = fmaf(l, r4.w, a3);
+                }
+                float *o = out + (size_t)co * KDP + t * Cg + j4;
+                o[0] = -a0;
+                if (j4 + 1 < Cg) o[1] = -a1;
+                if (j4 + 2 < Cg) o[2] = -a2;
+                if (j4 + 3 < Cg) o[3] = -a3;
+            }
+            continue;
+        }
         for (int e = tid; e < Cg * Cg; e += kPrepThreads) {
             const int r = e / Cg, c = e - r * Cg;
             Wq[r * TS + c] = __ldg(wg + r * row_stride + c * tap_stride + a);
@@ -116,7 +177,7 @@ int launch_prepare(const Geometry &g, const float *weight, float *prepared, cuda
                    size_t weight_stride, size_t prepared_stride)
 {
     if (count <= 0) return 0;
-    const size_t smem = (size_t)3 * g.Cg * (g.Cg + 1) * sizeof(float);
+    const size_t smem = prepare_smem_bytes(g.Cg);
     if (smem > (size_t)kMaxSmemBytes) return IFK_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -128,10 +189,13 @@ int launch_prepare(const Geometry &g, const float *weight, float *prepared, cuda
     int taps_per_cta = 1;
     while ((long)g.groups * count * 2 * ((g.K + taps_per_cta - 1) / taps_per_cta) > 8L * kNumSM && taps_per_cta < g.K)
         taps_per_cta++;
+    const EnvKnobs &knobs = env();
+    if (knobs.prep_cfg[1] > 0) taps_per_cta = knobs.prep_cfg[1] < g.K ? knobs.prep_cfg[1] : g.K;
+    const int tiled = knobs.prep_cfg[0] == 1 ? 0 : 1;
     dim3 grid(g.groups * count, 2, (g.K + taps_per_cta - 1) / taps_per_cta);
     prepare_kernel<<<grid, kPrepThreads, smem, s>>>(weight, prepared, g.C, g.Cg, g.Cw, g.KH, g.KW, g.KD,
                                                     g.KDP, taps_per_cta, g.groups, weight_stride,
-                                                    prepared_stride);
+                                                    prepared_stride, tiled);
     const int st = cuda_status(cudaGetLastError());
     if (st != 0) return st;
     // the pipelined wavefront kernel reads a lane-major packed copy of these rows (ifk_solve_wave.cu)

@@ -122,6 +122,7 @@ solve_wave_kernel(const WaveParams p)
     typedef WaveCfg<CG, KH, KW, CC, NS, VEC> Cfg;
     constexpr int LPP = Cfg::LPP, CGV = Cfg::CGV, NVF = Cfg::NVF, NVO = Cfg::NVO, PF = Cfg::PF, PO = Cfg::PO;
     constexpr int OWN = Cfg::OWN, NW4 = Cfg::NW4;
+    constexpr int TU = VEC == 2 ? 3 : 2;   // vectors per batch of the transposing passes (larger batches cost the loop registers: ptxas then adds moves to it)
     IFK_WPROBE(0);
     extern __shared__ __align__(128) float smem[];
     const int H = p.H, W = p.W, HW = p.H * p.W, PS = p.PS, RSP = p.RSP;
@@ -164,31 +165,25 @@ solve_wave_kernel(const WaveParams p)
         }
     };
 
-    // Programmatic dependent launch.  The prepared weights may be fetched ahead of the dependency
-    // wait only when the caller vouches that the previous operation of the stream did not write them
-    // (IFK_FLAG_STABLE_PREPARED); the dependents are released AFTER the wait, so that "the kernel
-    // before my predecessor has completed and is visible" holds transitively for them.  Either way the
-    // weight fetch (one L2 round trip) is in flight while the image lands and is transposed: nothing
-    // below needs the weights before the wavefront starts.
+    // Programmatic dependent launch.  Everything that touches only this CTA's shared memory or
+    // registers -- mbarrier init, the zero halo, the pinned loop constants -- runs AHEAD of the
+    // dependency wait, i.e. while the predecessor on the stream is still inside its wavefront; behind
+    // the wait only the image load is left on the launch-to-launch critical path.  The prepared weights
+    // may be fetched ahead of the wait only when the caller vouches that the previous operation of the
+    // stream did not write them (IFK_FLAG_STABLE_PREPARED); the dependents are released AFTER the wait,
+    // so that "the kernel before my predecessor has completed and is visible" holds transitively for
+    // them.  Either way the weight fetch (one L2 round trip) is in flight while the image lands and is
+    // transposed: nothing below needs the weights before the wavefront starts.
     if (p.early) { load_weights(0); load_offsets(); }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    int b = blockIdx.x;
-    if (p.bulk && tid == 0) {
-        mbar_init(bar, 1);
-        if (b < p.B) {
-            mbar_expect_tx(bar, img_bytes);
-            bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
-        }
+    if (tid == 0) {
+        if (p.bulk) mbar_init(bar, 1);
+        smem[2] = 0.f;                    // source of the opaque zero used by Hold
     }
-    if (tid == 0) smem[2] = 0.f;          // source of the opaque zero used by Hold
-    if (!p.early) { load_weights(0); load_offsets(); }
     // zero halo (and the extra column the look-ahead touches): once per CTA -- the interior of xh is
     // rewritten for every image, the interior of yb is written before it is read
     for (int i = tid * 4; i < 2 * p.YN; i += nthr * 4)
         *reinterpret_cast<float4 *>(yb + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();            // zero fill and mbarrier init visible
-    IFK_WPROBE(1);
 
     // which of the tile's CC output channels this lane finishes after the reduce-scatter
     int own_off, own_size;
@@ -209,7 +204,16 @@ solve_wave_kernel(const WaveParams p)
     // the transposing passes: TM pixel lanes x TC channel lanes
     const int TM = 1 << p.tm_shift, TC = nthr >> p.tm_shift;
     const int tm = tid & (TM - 1), tc = tid >> p.tm_shift;
+    IFK_WPROBE(1);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     IFK_WPROBE(2);
+    int b = blockIdx.x;
+    if (p.bulk && tid == 0 && b < p.B) {
+        mbar_expect_tx(bar, img_bytes);
+        bulk_load(xbuf, in0 + (size_t)b * img_stride, img_bytes, bar);
+    }
+    if (!p.early) { load_weights(0); load_offsets(); }
 
     uint32_t parity = 0;
     for (; b < p.B; b += gridDim.x) {
@@ -256,10 +260,22 @@ solve_wave_kernel(const WaveParams p)
                 }
                 continue;
             }
-#pragma unroll 2
-            for (int cv = tc; cv < CGV; cv += TC, d += dstep, sp += sstep) {
-                if (VEC == 4) *reinterpret_cast<float4 *>(d) = make_float4(sp[0], sp[HW], sp[2 * HW], sp[3 * HW]);
-                else *reinterpret_cast<float2 *>(d) = make_float2(sp[0], sp[HW]);
+            // (loads of a whole batch of vectors are issued before its first store: load/store pairs would
+            //  serialise on the shared-memory latency, ptxas does not move loads above stores it cannot disambiguate)
+            for (int cv = tc; cv < CGV; cv += TU * TC, d += TU * dstep, sp += TU * sstep) {
+                float t[TU][VEC];
+#pragma unroll
+                for (int u = 0; u < TU; u++)
+                    if (cv + u * TC < CGV) {
+#pragma unroll
+                        for (int e = 0; e < VEC; e++) t[u][e] = sp[u * sstep + e * HW];
+                    }
+#pragma unroll
+                for (int u = 0; u < TU; u++)
+                    if (cv + u * TC < CGV) {
+                        if (VEC == 4) *reinterpret_cast<float4 *>(d + u * dstep) = make_float4(t[u][0], t[u][1], t[u][2], t[u][3]);
+                        else *reinterpret_cast<float2 *>(d + u * dstep) = make_float2(t[u][0], t[u][1]);
+                    }
             }
         }
         __syncthreads();
@@ -377,17 +393,29 @@ solve_wave_kernel(const WaveParams p)
                 }
                 continue;
             }
-#pragma unroll 2
-            for (int cv = tc; cv < CGV; cv += TC, sp += sstep, xn += sstep, d += dstep) {
-                if (VEC == 4) {
-                    const float4 t4 = *reinterpret_cast<const float4 *>(sp);
-                    d[0] = t4.x; d[HW] = t4.y; d[2 * HW] = t4.z; d[3 * HW] = t4.w;
-                    if (more) *reinterpret_cast<float4 *>(xn) = t4;
-                } else {
-                    const float2 t2 = *reinterpret_cast<const float2 *>(sp);
-                    d[0] = t2.x; d[HW] = t2.y;
-                    if (more) *reinterpret_cast<float2 *>(xn) = t2;
-                }
+            for (int cv = tc; cv < CGV; cv += TU * TC, sp += TU * sstep, xn += TU * sstep, d += TU * dstep) {
+                float t[TU][VEC];
+#pragma unroll
+                for (int u = 0; u < TU; u++)
+                    if (cv + u * TC < CGV) {
+                        if (VEC == 4) {
+                            const float4 t4 = *reinterpret_cast<const float4 *>(sp + u * sstep);
+                            t[u][0] = t4.x; t[u][1] = t4.y; t[u][2] = t4.z; t[u][3] = t4.w;
+                        } else {
+                            const float2 t2 = *reinterpret_cast<const float2 *>(sp + u * sstep);
+                            t[u][0] = t2.x; t[u][1] = t2.y;
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < TU; u++)
+                    if (cv + u * TC < CGV) {
+#pragma unroll
+                        for (int e = 0; e < VEC; e++) d[u * dstep + e * HW] = t[u][e];
+                        if (more) {
+                            if (VEC == 4) *reinterpret_cast<float4 *>(xn + u * sstep) = make_float4(t[u][0], t[u][1], t[u][2], t[u][3]);
+                            else *reinterpret_cast<float2 *>(xn + u * sstep) = make_float2(t[u][0], t[u][1]);
+                        }
+                    }
             }
         }
         if (more) __syncthreads();                 // xh holds the next layer's input; yb may be overwritten

@@ -442,6 +442,45 @@ def test_window_kernel(IF, shape, monkeypatch):
     assert_parity(run_all(IF, x, w, g, groups))
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 3, 3, 1), (3, 3, 2, 2, 1), (5, 7, 3, 3, 1), (12, 12, 3, 3, 1), (13, 13, 3, 2, 1),
+                                   (24, 24, 3, 3, 4), (48, 48, 3, 3, 1), (48, 48, 5, 5, 4), (96, 96, 3, 3, 1), (20, 20, 1, 3, 2)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_tiled_prepare_matches_the_plain_loop_and_the_float64_fold(IF, shape, monkeypatch):
+    """ifk_prepare.cu: the register-tiled product (default) against the plain loop it replaces (IFK_PREP_CFG=1,...),
+    for every slab size, and both against T = (I + A0)^-1, -T W_q formed in float64 from the same weights"""
+    C, Cw, KH, KW, groups = shape
+    rng = np.random.default_rng(41)
+    w = make_weight(rng, C, Cw, KH, KW, 0.05)
+    wt = dev(w)
+    Cg, K = C // groups, KH * KW
+    KD = K * Cg
+    KDP = (KD + 3) // 4 * 4
+
+    def canonical(cfg):
+        if cfg:
+            monkeypatch.setenv("IFK_PREP_CFG", cfg)
+        buf = IF.Prepared(wt, groups).buffer
+        torch.cuda.synchronize()
+        return buf[:2 * C * KDP].cpu().numpy().reshape(2, C, KDP)[:, :, :KD].reshape(2, groups, Cg, K, Cg)
+
+    tiled = canonical(None)
+    for cfg in ("0,2", "0,%d" % K, "1,0", "1,3"):
+        other = canonical(cfg)
+        np.testing.assert_allclose(other, tiled, rtol=0, atol=2e-6 * max(1.0, np.abs(tiled).max()), err_msg=cfg)
+    w64 = w.astype(np.float64)
+    for G in range(groups):
+        blk = w64[G * Cg:(G + 1) * Cg, :Cg]                      # rows of the group, its Cg input columns
+        A0 = np.tril(blk[:, :, KH - 1, KW - 1], -1)
+        T = np.linalg.inv(np.eye(Cg) + A0)
+        for t in range(K):
+            Wq = blk[:, :, KH - 1 - t // KW, KW - 1 - t % KW]
+            fwd = T if t == 0 else -(T @ Wq)
+            adj = T.T if t == 0 else -(T.T @ Wq.T)
+            for d, ref in ((0, fwd), (1, adj)):
+                err = np.abs(tiled[d, G, :, t, :] - ref).max() / max(np.abs(ref).max(), 1e-30)
+                assert err < 1e-5, (G, t, d, err)
+
+
 def test_weight_with_fewer_input_columns(IF):
     """groups=4 only reads W[:, :C/4]; a (C, C/4, k, k) weight must give the same result."""
     rng = np.random.default_rng(2)

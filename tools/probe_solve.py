@@ -21,6 +21,9 @@ from inverse_flow_b200.stack import reference_init_weight  # noqa: E402
 
 NAMES = ["start -> prologue done", "bookkeeping", "loop constants", "wait for the image (TMA)",
          "pre-pass / transpose", "diagonal loop", "write-out", "tail"]
+# the wave kernel does everything that needs no global data ahead of the dependency wait
+WAVE_NAMES = ["start -> pre-wait prologue done", "dependency wait + release", "image load issued", "wait for the image (TMA)",
+              "transpose", "diagonal loop", "write-out", "tail"]
 
 
 def main():
@@ -52,7 +55,7 @@ def main():
     print((B, C, H, W, k, g), _native.describe_solve(p))
     ndiag = H + W - 1
     if t[8] > t[0]:
-        for a, name in enumerate(NAMES):
+        for a, name in enumerate(WAVE_NAMES if _native.describe_solve(p).startswith("wave<") else NAMES):
             if t[a + 1] - t[a] > 0:
                 print("  %-34s %8d cycles" % (name, t[a + 1] - t[a]))
         print("  total %d cycles; %.1f cycles per diagonal (%d diagonals)" % (t[8] - t[0], (t[6] - t[5]) / ndiag, ndiag))
