@@ -13,7 +13,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libifk_b200.so")
+# IFK_LIBRARY: another build of the same ABI (development: tools/variant_build.py A/B-tests compile-time variants)
+LIB_PATH = os.environ.get("IFK_LIBRARY") or os.path.join(_PKG, "lib", "libifk_b200.so")
 
 EXPORTS = (
     "ifk_version", "ifk_status_string", "ifk_prepared_floats", "ifk_prepare_f32", "ifk_prepare_many_f32",

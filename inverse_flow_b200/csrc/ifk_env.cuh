@@ -24,7 +24,7 @@ struct EnvKnobs {
     int wave_cfg[4];     // IFK_WAVE_CFG="cc,ns,vec,threads" (0 = unset) : tuning
     int dw_cfg[2];       // IFK_DW_CFG="warps,ctas"       (0 = unset) : tuning of the quad dW kernel
     int split_cfg[2];    // IFK_SPLIT_CFG="nsh"            (0 = unset) : tuning
-    int prep_cfg[2];     // IFK_PREP_CFG="legacy,taps"    : legacy = 1 pins the untiled product loop; taps per CTA (0 = unset)
+    int prep_cfg[2];     // IFK_PREP_CFG="0,taps"         : taps per CTA of the tap products (0 = unset; first field reserved) : tuning
     bool pins_other_solver() const { return solve_global || solve_stream || solve_window || has_solve_cfg; }
 };
 

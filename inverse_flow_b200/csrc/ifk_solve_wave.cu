@@ -430,74 +430,69 @@ solve_wave_kernel(const WaveParams p)
 // for lane l = (ct, ks) of a pixel the flat pair index f = i*CC + cc (i-th packed pair of the lane's reduction
 // slice, output channel ct*CC + cc) lands in float4 number f/2 -- stored [f/2][l], so that a warp's loads are
 // consecutive 16-byte words.  `codes` gets, once per direction-independent geometry, the neighbour each vector
-// entry of a lane reads.  One thread per (layer, dir, group, lane, pair).
+// entry of a lane reads.  One thread per (layer, dir, group) x (float4, lane): consecutive threads write consecutive
+// 16-byte words; the tap of an "old" entry comes from a table the host fills (this kernel sits on the critical path
+// in front of a step's first solve: the first version, one thread per pair with a tap search and ~20 integer
+// divisions each, took 27 us for 48 layers of Cg = 48).
 struct WavePackParams {
     const float *prepared;   // canonical, [layer][dir][group][co][KDP]
     float *pack;             // [layer][dir][group][NW4][LPP] float4
     size_t pack_floats;      // floats of one layer's pack; its codes ([(NVF+NVO)][LPP] ints) follow
     size_t prepared_stride, pack_stride;      // floats between layers (pack_stride: of the pack section)
     int C, cg, kh, kw, cc, ns, vec, KDP, groups, count;
+    int aligned;                              // every layer's pack starts at a multiple of 16 bytes
+    unsigned char old_tap[64];                // i-th tap (array order) that lies two or more diagonals back
 };
 
 __global__ void __launch_bounds__(256)
 wave_pack_kernel(const WavePackParams q)
 {
-    const int K = q.kh * q.kw, cgv = q.cg / q.vec, nct = q.cg / q.cc, lpp = nct * q.ns;
+    const int K = q.kh * q.kw, cgv = q.cg / q.vec, nct = q.cg / q.cc, lpp = nct * q.ns, hv = q.vec >> 1;
     const int nft = (q.kw > 1) + (q.kh > 1), not_ = K - 1 - nft;
     const int NF = nft * cgv, NO = (not_ + 1) * cgv;
     const int nvf = (NF + q.ns - 1) / q.ns, nvo = (NO + q.ns - 1) / q.ns;
-    const int pf = nvf * q.vec / 2, po = nvo * q.vec / 2;
+    const int pf = nvf * hv, po = nvo * hv;
     const int npairs = q.cc * (pf + po), nw4 = (npairs + 1) / 2;
-    const long total = (long)q.count * 2 * q.groups * lpp * (2 * nw4);
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        long r = e;
-        const int f = (int)(r % (2 * nw4)); r /= 2 * nw4;        // flat pair index (the pad pair of an odd count too)
-        const int l = (int)(r % lpp); r /= lpp;
-        const int G = (int)(r % q.groups); r /= q.groups;
-        const int dir = (int)(r % 2);
-        const int layer = (int)(r / 2);
-        const int ks = l % q.ns, ct = l / q.ns;
-        float w0 = 0.f, w1 = 0.f;
-        int code = 0, slot_j = -1;
-        if (f < npairs) {
-            const int i = f / q.cc, cc = f - i * q.cc;           // i-th packed pair of the slice
-            const bool fresh = i < pf;
-            const int ip = fresh ? i : i - pf;
-            const int j = ip / (q.vec / 2), e2 = ip - j * (q.vec / 2);      // vector entry slot, pair inside it
-            const int ent = j * q.ns + ks;
-            const bool valid = ent < (fresh ? NF : NO);
-            if (valid) {
-                const int ti = ent / cgv, qv = ent - ti * cgv;
-                int t = 0;
-                bool is_x = false;
-                if (fresh) t = (q.kw > 1 && ti == 0) ? 1 : q.kw;
-                else if (ti == not_) is_x = true;
-                else {
-                    int n = 0;
-                    for (int tt = 1; tt < K; tt++) {
-                        if (tt / q.kw + tt % q.kw < 2) continue;
-                        if (n == ti) { t = tt; break; }
-                        n++;
-                    }
-                }
-                const float *src = q.prepared + (size_t)layer * q.prepared_stride +
-                                   ((size_t)dir * q.C + (size_t)G * q.cg + ct * q.cc + cc) * q.KDP + t * q.cg +
-                                   qv * q.vec + 2 * e2;
-                w0 = src[0];
-                w1 = src[1];
-                code = wave_code(t / q.kw, t % q.kw, qv * q.vec, is_x);
-                if (cc == 0 && e2 == 0 && dir == 0 && G == 0) slot_j = (fresh ? 0 : nvf) + j;
-            } else if (cc == 0 && e2 == 0 && dir == 0 && G == 0) {
-                slot_j = (fresh ? 0 : nvf) + j;                 // padding entry: offset 0, zero weights
-            }
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nw4 * lpp) return;
+    const int f2 = e / lpp, l = e - f2 * lpp;                    // float4 number, lane
+    const int G = blockIdx.y % q.groups, r = blockIdx.y / q.groups;
+    const int dir = r & 1, layer = r >> 1;
+    const int ks = l % q.ns, ct = l / q.ns;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int f = 2 * f2 + h;                                // flat pair index (the pad pair of an odd count too)
+        if (f >= npairs) continue;
+        const int i = f / q.cc, cc = f - i * q.cc;               // i-th packed pair of the slice
+        const bool fresh = i < pf;
+        const int ip = fresh ? i : i - pf;
+        const int j = hv == 1 ? ip : ip >> 1, e2 = hv == 1 ? 0 : ip & 1;     // vector entry slot, pair inside it
+        const int ent = j * q.ns + ks;
+        const bool valid = ent < (fresh ? NF : NO);
+        int code = 0;
+        if (valid) {
+            const int ti = ent / cgv, qv = ent - ti * cgv;
+            int t = 0;
+            bool is_x = false;
+            if (fresh) t = (q.kw > 1 && ti == 0) ? 1 : q.kw;
+            else if (ti == not_) is_x = true;
+            else t = q.old_tap[ti];
+            const float *src = q.prepared + (size_t)layer * q.prepared_stride +
+                               ((size_t)dir * q.C + (size_t)G * q.cg + ct * q.cc + cc) * q.KDP + t * q.cg +
+                               qv * q.vec + 2 * e2;
+            w[2 * h] = src[0];
+            w[2 * h + 1] = src[1];
+            const int th = t / q.kw;
+            code = wave_code(th, t - th * q.kw, qv * q.vec, is_x);
         }
-        float *dstp = q.pack + (size_t)layer * q.pack_stride + (((size_t)dir * q.groups + G) * nw4 + f / 2) * lpp * 4 +
-                      (size_t)l * 4 + (f & 1) * 2;
-        dstp[0] = w0;
-        dstp[1] = w1;
-        if (slot_j >= 0)
-            reinterpret_cast<int *>(q.pack + (size_t)layer * q.pack_stride + q.pack_floats)[(size_t)slot_j * lpp + l] = code;
+        // (padding entries: offset 0, zero weights)
+        if (cc == 0 && e2 == 0 && dir == 0 && G == 0)
+            reinterpret_cast<int *>(q.pack + (size_t)layer * q.pack_stride + q.pack_floats)[(size_t)((fresh ? 0 : nvf) + j) * lpp + l] = code;
     }
+    float *dstp = q.pack + (size_t)layer * q.pack_stride + (((size_t)dir * q.groups + G) * nw4 + f2) * lpp * 4 + (size_t)l * 4;
+    if (q.aligned) *reinterpret_cast<float4 *>(dstp) = make_float4(w[0], w[1], w[2], w[3]);
+    else { dstp[0] = w[0]; dstp[1] = w[1]; dstp[2] = w[2]; dstp[3] = w[3]; }     // (such a buffer is refused by the solve)
 }
 
 // ---- host side -----------------------------------------------------------------------------
@@ -737,10 +732,15 @@ int launch_wave_pack(const Geometry &g, float *prepared, int count, size_t prepa
     q.pack_stride = prepared_stride;
     q.C = g.C; q.cg = v->cg; q.kh = v->kh; q.kw = v->kw; q.cc = v->cc; q.ns = v->ns; q.vec = v->vec;
     q.KDP = g.KDP; q.groups = g.groups; q.count = count;
-    const long total = (long)count * 2 * g.groups * d.lpp * (2 * d.nw4);
-    long blocks = (total + 255) / 256;
-    if (blocks > 8L * device_sm_count()) blocks = 8L * device_sm_count();
-    wave_pack_kernel<<<(unsigned)blocks, 256, 0, s>>>(q);
+    {   // taps two or more diagonals back, in array order (wave_gather_cost enumerates them the same way)
+        int n = 0;
+        for (int tt = 1; tt < g.K && n < 64; tt++)
+            if (tt / v->kw + tt % v->kw >= 2) q.old_tap[n++] = (unsigned char)tt;
+    }
+    if (g.K > 64 || (long)count * 2 * g.groups > 65535) return IFK_ERR_UNSUPPORTED;
+    q.aligned = ((uintptr_t)q.pack % 16 == 0 && (count == 1 || prepared_stride % 4 == 0)) ? 1 : 0;
+    dim3 grid((unsigned)((d.nw4 * d.lpp + 255) / 256), (unsigned)(count * 2 * g.groups));
+    wave_pack_kernel<<<grid, 256, 0, s>>>(q);
     return cuda_status(cudaGetLastError());
 }
 

@@ -445,9 +445,9 @@ def test_window_kernel(IF, shape, monkeypatch):
 @pytest.mark.parametrize("shape", [(1, 1, 3, 3, 1), (3, 3, 2, 2, 1), (5, 7, 3, 3, 1), (12, 12, 3, 3, 1), (13, 13, 3, 2, 1),
                                    (24, 24, 3, 3, 4), (48, 48, 3, 3, 1), (48, 48, 5, 5, 4), (96, 96, 3, 3, 1), (20, 20, 1, 3, 2)],
                          ids=lambda s: "x".join(map(str, s)))
-def test_tiled_prepare_matches_the_plain_loop_and_the_float64_fold(IF, shape, monkeypatch):
-    """ifk_prepare.cu: the register-tiled product (default) against the plain loop it replaces (IFK_PREP_CFG=1,...),
-    for every slab size, and both against T = (I + A0)^-1, -T W_q formed in float64 from the same weights"""
+def test_prepared_rows_match_the_float64_fold_for_every_slab_size(IF, shape, monkeypatch):
+    """ifk_prepare.cu: the canonical prepared rows (T kernel + register-tiled tap products) for every slab size of
+    the tap launch (IFK_PREP_CFG=0,n), against T = (I + A0)^-1, -T W_q formed in float64 from the same weights"""
     C, Cw, KH, KW, groups = shape
     rng = np.random.default_rng(41)
     w = make_weight(rng, C, Cw, KH, KW, 0.05)
@@ -464,9 +464,8 @@ def test_tiled_prepare_matches_the_plain_loop_and_the_float64_fold(IF, shape, mo
         return buf[:2 * C * KDP].cpu().numpy().reshape(2, C, KDP)[:, :, :KD].reshape(2, groups, Cg, K, Cg)
 
     tiled = canonical(None)
-    for cfg in ("0,2", "0,%d" % K, "1,0", "1,3"):
-        other = canonical(cfg)
-        np.testing.assert_allclose(other, tiled, rtol=0, atol=2e-6 * max(1.0, np.abs(tiled).max()), err_msg=cfg)
+    for cfg in ("0,1", "0,2", "0,%d" % K):
+        assert np.array_equal(canonical(cfg), tiled), cfg           # the slab size only changes which CTA forms a tap
     w64 = w.astype(np.float64)
     for G in range(groups):
         blk = w64[G * Cg:(G + 1) * Cg, :Cg]                      # rows of the group, its Cg input columns
