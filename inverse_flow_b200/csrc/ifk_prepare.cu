@@ -53,6 +53,27 @@ struct PrepParams {
     int C, Cg, Cw, KH, KW, KD, KDP, groups, taps_per_cta;
 };
 
+// Column j of T = (I + A0)^-1 with the column in REGISTERS (compile-time group width): row i only needs the
+// thread's own earlier entries, so the shared-memory round trip per multiply-add of the generic loop (store T[i][j],
+// load it back for every later row: ~30 us for 48 layers of Cg = 48) shrinks to one broadcast load of A[i][k];
+// four partial sums as in the generic loop.  All lanes run the same instruction stream (entries above the diagonal
+// are computed as sums of zeros and then forced to +0).
+template <int CG>
+__device__ __forceinline__ void t_column_in_registers(const float *A, float *T, int TS, int j)
+{
+    float t[CG];
+#pragma unroll
+    for (int i = 0; i < CG; i++) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < i; k++) s[k & 3] = fmaf(A[i * TS + k], t[k], s[k & 3]);
+        const float v = -((s[0] + s[1]) + (s[2] + s[3]));
+        t[i] = i < j ? 0.f : (i == j ? 1.f : v);
+    }
+#pragma unroll
+    for (int i = 0; i < CG; i++) T[i * TS + j] = t[i];
+}
+
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_t_kernel(const PrepParams q)
 {
@@ -67,6 +88,9 @@ prepare_t_kernel(const PrepParams q)
     const float *wg = q.weight + (size_t)layer * q.weight_stride + (size_t)G * Cg * row_stride;
     const int centre = K - 1;                              // array index of shift (0,0)
     const int tid = threadIdx.x;
+    // programmatic dependent launch: the tap kernel behind this one may be scheduled now (its launch latency and
+    // shared-memory set-up overlap the substitution); it waits for this grid before it reads T
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     for (int e = tid; e < Cg * Cg; e += kPrepThreads) {
         const int i = e / Cg, k = e - i * Cg;
@@ -74,6 +98,17 @@ prepare_t_kernel(const PrepParams q)
     }
     __syncthreads();
     // column j of T0 by forward substitution: T[i][j] = [i==j] - sum_{j<=k<i} A[i][k] T[k][j]
+    const bool in_registers = Cg == 6 || Cg == 12 || Cg == 24 || Cg == 48;       // the reference models' group widths
+    if (in_registers) {
+        if (tid < Cg) {
+            switch (Cg) {
+                case 6: t_column_in_registers<6>(A, T, TS, tid); break;
+                case 12: t_column_in_registers<12>(A, T, TS, tid); break;
+                case 24: t_column_in_registers<24>(A, T, TS, tid); break;
+                default: t_column_in_registers<48>(A, T, TS, tid); break;
+            }
+        }
+    } else
     for (int j = tid; j < Cg; j += kPrepThreads) {
         for (int i = 0; i < j; i++) T[i * TS + j] = 0.f;
         T[j * TS + j] = 1.f;
@@ -121,13 +156,17 @@ prepare_taps_kernel(const PrepParams q)
     float *out = q.prepared + (size_t)layer * q.prepared_stride + ((size_t)dir * q.C + (size_t)G * Cg) * KDP;
     const int tid = threadIdx.x;
 
-    for (int e = tid; e < Cg * Cg; e += kPrepThreads) {
-        const int co = e / Cg, k = e - co * Cg;
-        L[co * TS + k] = out[(size_t)co * KDP + k];        // written by prepare_t_kernel (the launch before)
-    }
     for (int e = tid; e < Cg * (RS - Cg); e += kPrepThreads) {   // pad columns: read by the last tile, never written again
         const int k = e / (RS - Cg);
         Wq[k * RS + Cg + (e - k * (RS - Cg))] = 0.f;
+    }
+    // T comes from the launch before (prepare_t_kernel); dependents (the pack kernel) are released after the wait, so
+    // that "everything before my predecessor is complete" holds for them too
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int e = tid; e < Cg * Cg; e += kPrepThreads) {
+        const int co = e / Cg, k = e - co * Cg;
+        L[co * TS + k] = out[(size_t)co * KDP + k];
     }
     const int t_begin = 1 + blockIdx.z * q.taps_per_cta;
     const int t_end = t_begin + q.taps_per_cta < K ? t_begin + q.taps_per_cta : K;
@@ -149,7 +188,24 @@ prepare_taps_kernel(const PrepParams q)
             const float *lp = L + co * TS;
             const float *rp = Wq + j4;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            for (int k = k0; k < k1; k++) {
+            int k = k0;
+            for (; k + 3 < k1; k += 4) {               // the eight loads of four steps in flight together
+                float l[4];
+                float4 r4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    l[u] = lp[k + u];
+                    r4[u] = *reinterpret_cast<const float4 *>(rp + (k + u) * RS);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    a0 = fmaf(l[u], r4[u].x, a0);
+                    a1 = fmaf(l[u], r4[u].y, a1);
+                    a2 = fmaf(l[u], r4[u].z, a2);
+                    a3 = fmaf(l[u], r4[u].w, a3);
+                }
+            }
+            for (; k < k1; k++) {
                 const float l = lp[k];
                 const float4 r4 = *reinterpret_cast<const float4 *>(rp + k * RS);
                 a0 = fmaf(l, r4.x, a0);
@@ -193,9 +249,17 @@ int launch_prepare(const Geometry &g, const float *weight, float *prepared, cuda
         const EnvKnobs &knobs = env();
         if (knobs.prep_cfg[1] > 0) taps_per_cta = knobs.prep_cfg[1] < g.K - 1 ? knobs.prep_cfg[1] : g.K - 1;
         q.taps_per_cta = taps_per_cta;
-        dim3 grid(g.groups * count, 2, (g.K - 1 + taps_per_cta - 1) / taps_per_cta);
-        prepare_taps_kernel<<<grid, kPrepThreads, smem, s>>>(q);
-        st = cuda_status(cudaGetLastError());
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(g.groups * count, 2, (g.K - 1 + taps_per_cta - 1) / taps_per_cta);
+        cfg.blockDim = dim3(kPrepThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = env().pdl ? 1 : 0;
+        st = cuda_status(cudaLaunchKernelEx(&cfg, prepare_taps_kernel, q));
         if (st != 0) return st;
     }
     // the pipelined wavefront kernel reads a lane-major packed copy of these rows (ifk_solve_wave.cu)

@@ -454,6 +454,7 @@ wave_pack_kernel(const WavePackParams q)
     const int pf = nvf * hv, po = nvo * hv;
     const int npairs = q.cc * (pf + po), nw4 = (npairs + 1) / 2;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // the canonical rows come from the launch(es) before
     if (e >= nw4 * lpp) return;
     const int f2 = e / lpp, l = e - f2 * lpp;                    // float4 number, lane
     const int G = blockIdx.y % q.groups, r = blockIdx.y / q.groups;
@@ -739,9 +740,16 @@ int launch_wave_pack(const Geometry &g, float *prepared, int count, size_t prepa
     }
     if (g.K > 64 || (long)count * 2 * g.groups > 65535) return IFK_ERR_UNSUPPORTED;
     q.aligned = ((uintptr_t)q.pack % 16 == 0 && (count == 1 || prepared_stride % 4 == 0)) ? 1 : 0;
-    dim3 grid((unsigned)((d.nw4 * d.lpp + 255) / 256), (unsigned)(count * 2 * g.groups));
-    wave_pack_kernel<<<grid, 256, 0, s>>>(q);
-    return cuda_status(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((d.nw4 * d.lpp + 255) / 256), (unsigned)(count * 2 * g.groups));
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // scheduled while the prepare kernels still run
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = env().pdl ? 1 : 0;
+    return cuda_status(cudaLaunchKernelEx(&cfg, wave_pack_kernel, q));
 }
 
 // one launch over `n` consecutive layers (n == 1: a plain solve).  prepared[i]: layer i's whole prepared buffer.
