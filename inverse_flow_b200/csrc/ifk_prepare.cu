@@ -98,11 +98,13 @@ prepare_t_kernel(const PrepParams q)
     }
     __syncthreads();
     // column j of T0 by forward substitution: T[i][j] = [i==j] - sum_{j<=k<i} A[i][k] T[k][j]
-    const bool in_registers = Cg == 6 || Cg == 12 || Cg == 24 || Cg == 48;       // the reference models' group widths
+    const bool in_registers = Cg == 4 || Cg == 6 || Cg == 8 || Cg == 12 || Cg == 24 || Cg == 48;   // the reference models' group widths
     if (in_registers) {
         if (tid < Cg) {
             switch (Cg) {
+                case 4: t_column_in_registers<4>(A, T, TS, tid); break;
                 case 6: t_column_in_registers<6>(A, T, TS, tid); break;
+                case 8: t_column_in_registers<8>(A, T, TS, tid); break;
                 case 12: t_column_in_registers<12>(A, T, TS, tid); break;
                 case 24: t_column_in_registers<24>(A, T, TS, tid); break;
                 default: t_column_in_registers<48>(A, T, TS, tid); break;

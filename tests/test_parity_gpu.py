@@ -442,7 +442,7 @@ def test_window_kernel(IF, shape, monkeypatch):
     assert_parity(run_all(IF, x, w, g, groups))
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 3, 3, 1), (3, 3, 2, 2, 1), (5, 7, 3, 3, 1), (12, 12, 3, 3, 1), (13, 13, 3, 2, 1),
+@pytest.mark.parametrize("shape", [(1, 1, 3, 3, 1), (3, 3, 2, 2, 1), (4, 4, 2, 2, 1), (8, 8, 2, 2, 1), (5, 7, 3, 3, 1), (12, 12, 3, 3, 1), (13, 13, 3, 2, 1),
                                    (24, 24, 3, 3, 4), (48, 48, 3, 3, 1), (48, 48, 5, 5, 4), (96, 96, 3, 3, 1), (20, 20, 1, 3, 2)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_prepared_rows_match_the_float64_fold_for_every_slab_size(IF, shape, monkeypatch):
