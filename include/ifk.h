@@ -101,7 +101,10 @@ const char *ifk_status_string(int status);
  * for the forward solve (L^-1) and, transposed, for the adjoint solve (L^-T).  Folding T
  * removes the per-pixel Cg-step channel substitution from the wavefront's critical path.
  * One ifk_prepare_f32 call serves one ifk_inverse_f32 and the matching ifk_backward_f32.
- * `prepared` must hold ifk_prepared_floats(p) floats. */
+ * `prepared` must hold ifk_prepared_floats(p) floats and should start at a multiple of 16 bytes
+ * (the model-shape solve kernels read their packed copy as 16-byte words and refuse an unaligned
+ * buffer with IFK_ERR_UNSUPPORTED).  Internally: T once per layer, the tap products, the packed
+ * copy -- three launches on `stream`, chained by programmatic dependent launch. */
 size_t ifk_prepared_floats(const ifk_problem *p);
 int ifk_prepare_f32(const ifk_problem *p, const float *weight, float *prepared,
                     ifk_stream_t stream);

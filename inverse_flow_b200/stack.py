@@ -89,9 +89,10 @@ class InvConvStack:
         self._sides_forked = []           # side streams forked since the last join (a graph capture must
                                           # only join streams that are part of it)
         self.graph = None
-        # per stage: prepare (+ the wave kernel's weight pack) + n inverse + n dX + n dW stage 1 + 1 dW stage 2
-        self.launches_per_step = sum(3 * st.n + 2 + (1 if "wave<" in _native.describe_solve(st.problem) else 0)
-                                     for st in self.stages)
+        # per stage: prepare (T kernel, tap products for k > 1, + the wave kernel's weight pack) + n inverse + n dX
+        # + n dW stage 1 + 1 dW stage 2
+        self.launches_per_step = sum(3 * st.n + 2 + (1 if st.k > 1 else 0) +
+                                     (1 if "wave<" in _native.describe_solve(st.problem) else 0) for st in self.stages)
 
     # -- raw launches ------------------------------------------------------------------
     def _stream(self):
