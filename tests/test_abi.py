@@ -224,3 +224,21 @@ def test_split_kernel_is_opt_in_and_limited_to_the_rows_it_holds(lib, monkeypatc
     with_split = lib.ifk_prepared_floats(ctypes.byref(p))
     monkeypatch.setenv("IFK_SOLVE_SPLIT", "0")
     assert lib.ifk_prepared_floats(ctypes.byref(p)) < with_split
+
+
+def test_library_override_fails_loudly_when_the_file_is_missing():
+    """IFK_LIBRARY (development: another build of the same ABI, tools/variant_build.py) replaces the in-tree path; a
+    missing file raises -- there is no fallback to the default build, let alone to a CPU path"""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from inverse_flow_b200 import _native\n"
+            "try:\n    _native.load()\nexcept _native.IfkError as e:\n    print('IfkError', 'not found' in str(e))\n" % ROOT)
+    env = dict(os.environ, IFK_LIBRARY="/nonexistent/libifk_variant.so")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.stdout.strip().endswith("IfkError True"), (out.stdout, out.stderr[-500:])
+    env = dict(os.environ, IFK_LIBRARY=_native.LIB_PATH)
+    code_ok = ("import sys; sys.path.insert(0, %r)\n"
+               "from inverse_flow_b200 import _native\nprint(_native.load().ifk_version())\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code_ok], env=env, capture_output=True, text=True, timeout=300)
+    assert out.stdout.strip().isdigit(), (out.stdout, out.stderr[-500:])
